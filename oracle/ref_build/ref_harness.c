@@ -481,3 +481,13 @@ TFREF_API void tfref_apply_block(int width, int height, int ss_x, int ss_y,
                               accum, count);
   free(mbd);
 }
+
+/* OD_DIVU (aom_dsp/odintrin.h:30-42) probes: single value, and an exhaustive
+ * comparison with plain integer division over d in [dmin,dmax], x in [0,xmax]. */
+TFREF_API unsigned tfref_od_divu(unsigned x, unsigned d) { return OD_DIVU(x, d); }
+TFREF_API long long tfref_od_divu_mismatches(unsigned dmin, unsigned dmax, unsigned xmax) {
+  long long bad = 0;
+  for (unsigned d = dmin; d <= dmax; d++)
+    for (unsigned x = 0; x <= xmax; x++) bad += (OD_DIVU(x, d) != x / d);
+  return bad;
+}
