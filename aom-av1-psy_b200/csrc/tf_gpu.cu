@@ -1,0 +1,729 @@
+// Host side of libtf_gpu.so: the C ABI declared in include/tf_gpu.h.
+//
+// Mirrors what av1_temporal_filter() (av1/encoder/temporal_filter.c:1276-1312)
+// does around the per-block loop: resolve the window into plain parameters,
+// make the frames available to the workers (here: device frame cache with
+// on-device border replication, the counterpart of av1_copy_and_extend_frame,
+// av1/encoder/extend.c:113), run all blocks (here: one CUDA grid instead of
+// the row job queue of av1/encoder/ethread.c:2062-2189), hand back the filtered
+// frame and FRAME_DIFF.  No CPU fallback: without a CUDA device every entry
+// point returns TF_GPU_ERR_NO_DEVICE.
+#include "tf_kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#pragma GCC visibility push(default)
+#include "../../include/tf_gpu.h"
+#pragma GCC visibility pop
+
+using namespace tfk;
+
+namespace {
+
+constexpr int DEV_BORDER = 64;  // luma device border (samples); see DESIGN.md "Data layout"
+
+struct Geometry {
+  int is_hbd, ss_x, ss_y, num_planes;
+  int crop_w[2], crop_h[2], aligned_w[2], aligned_h[2];
+  int bx[2], by[2], pitch[2], rows[2];
+  bool operator==(const Geometry &o) const { return memcmp(this, &o, sizeof(*this)) == 0; }
+};
+
+struct DevFrame {
+  uint64_t frame_id = 0;
+  uint64_t last_use = 0;
+  uint64_t pinned_epoch = 0;
+  bool valid = false;
+  Geometry g;
+  void *base[3] = { nullptr, nullptr, nullptr };  // allocation base
+  void *p00[3] = { nullptr, nullptr, nullptr };   // pixel (0,0)
+};
+
+struct Ticket {
+  uint64_t id = 0;
+  cudaEvent_t ev = nullptr;
+  int64_t *diff_dst = nullptr;
+  bool want_diff = false;
+  bool pending = false;
+};
+
+}  // namespace
+
+struct tf_gpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<DevFrame> cache;
+  DevFrame out;
+  uint64_t use_counter = 0, epoch = 0;
+  unsigned long long *d_diff = nullptr;   // [8][2] ring
+  unsigned long long *h_diff = nullptr;   // pinned mirror
+  unsigned long long *d_noise = nullptr;  // [2]
+  unsigned long long *h_noise = nullptr;
+  Ticket tickets[8];
+  uint64_t next_ticket = 1;
+  int last_launches = 0;
+  float last_kernel_ms = 0.f;
+  // dump buffers (device), grown on demand
+  void *d_dump[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+  size_t d_dump_sz[5] = { 0, 0, 0, 0, 0 };
+  char err[512] = { 0 };
+};
+
+namespace {
+
+int fail(tf_gpu_ctx *c, int code, const char *fmt, ...) {
+  if (c) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(c->err, sizeof(c->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess)                                                                           \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? TF_GPU_ERR_MEM : TF_GPU_ERR_CUDA, "%s: %s", \
+                  #call, cudaGetErrorString(e_));                                                    \
+  } while (0)
+
+int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+bool make_geometry(const tf_gpu_frame *f, int num_planes, Geometry *g) {
+  memset(g, 0, sizeof(*g));
+  g->is_hbd = f->is_hbd ? 1 : 0;
+  g->ss_x = f->ss_x;
+  g->ss_y = f->ss_y;
+  g->num_planes = num_planes;
+  for (int k = 0; k < 2; k++) {
+    g->crop_w[k] = f->crop_w[k];
+    g->crop_h[k] = f->crop_h[k];
+    g->aligned_w[k] = f->aligned_w[k];
+    g->aligned_h[k] = f->aligned_h[k];
+  }
+  if (f->crop_w[0] <= 0 || f->crop_h[0] <= 0 || f->ss_x < 0 || f->ss_x > 1 || f->ss_y < 0 || f->ss_y > 1) return false;
+  if (f->aligned_w[0] < f->crop_w[0] || f->aligned_h[0] < f->crop_h[0]) return false;
+  for (int k = 0; k < 2; k++) {
+    g->bx[k] = k ? DEV_BORDER >> f->ss_x : DEV_BORDER;
+    g->by[k] = k ? DEV_BORDER >> f->ss_y : DEV_BORDER;
+    g->pitch[k] = align_up(g->aligned_w[k] + 2 * g->bx[k], 128);
+    g->rows[k] = g->aligned_h[k] + 2 * g->by[k];
+  }
+  return true;
+}
+
+int alloc_dev_frame(tf_gpu_ctx *ctx, DevFrame *d, const Geometry &g) {
+  const size_t es = g.is_hbd ? 2 : 1;
+  if (d->base[0] && d->g == g) return TF_GPU_OK;
+  for (int p = 0; p < 3; p++) {
+    if (d->base[p]) cudaFree(d->base[p]);
+    d->base[p] = d->p00[p] = nullptr;
+  }
+  d->g = g;
+  d->valid = false;
+  for (int p = 0; p < g.num_planes; p++) {
+    const int k = p > 0;
+    const size_t bytes = (size_t)g.rows[k] * g.pitch[k] * es;
+    CU(cudaMalloc(&d->base[p], bytes));
+    d->p00[p] = (char *)d->base[p] + ((size_t)g.by[k] * g.pitch[k] + g.bx[k]) * es;
+  }
+  return TF_GPU_OK;
+}
+
+// Upload the crop area of a host frame and rebuild the borders on the device.
+int upload_frame(tf_gpu_ctx *ctx, DevFrame *d, const tf_gpu_frame *f) {
+  const Geometry &g = d->g;
+  const size_t es = g.is_hbd ? 2 : 1;
+  for (int p = 0; p < g.num_planes; p++) {
+    const int k = p > 0;
+    if (!f->plane[p]) return fail(ctx, TF_GPU_ERR_INVALID, "frame plane %d is NULL", p);
+    CU(cudaMemcpy2DAsync(d->p00[p], (size_t)g.pitch[k] * es, f->plane[p], (size_t)f->stride[k] * es,
+                         (size_t)g.crop_w[k] * es, g.crop_h[k], cudaMemcpyHostToDevice, ctx->stream));
+    const int ext_w = g.aligned_w[k] + g.bx[k], ext_h = g.aligned_h[k] + g.by[k];
+    const long long n = (long long)(g.bx[k] + ext_w) * (g.by[k] + ext_h);
+    const int threads = 256;
+    const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads);
+    if (g.is_hbd)
+      extend_borders_kernel<uint16_t><<<blocks, threads, 0, ctx->stream>>>((uint16_t *)d->p00[p], g.pitch[k],
+                                                                          g.crop_w[k], g.crop_h[k], g.bx[k], g.by[k],
+                                                                          ext_w, ext_h);
+    else
+      extend_borders_kernel<uint8_t><<<blocks, threads, 0, ctx->stream>>>((uint8_t *)d->p00[p], g.pitch[k],
+                                                                         g.crop_w[k], g.crop_h[k], g.bx[k], g.by[k],
+                                                                         ext_w, ext_h);
+    ctx->last_launches++;
+  }
+  CU(cudaGetLastError());
+  d->frame_id = f->frame_id;
+  d->valid = true;
+  return TF_GPU_OK;
+}
+
+DevFrame *find_cached(tf_gpu_ctx *ctx, uint64_t id, const Geometry *g) {
+  if (!id) return nullptr;
+  for (auto &d : ctx->cache)
+    if (d.valid && d.frame_id == id && (!g || d.g == *g)) return &d;
+  return nullptr;
+}
+
+// Returns a slot holding the frame (uploading if needed); the slot is pinned
+// for the current epoch so that one window never evicts its own frames.
+int get_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *f, int num_planes, DevFrame **out) {
+  Geometry g;
+  if (!make_geometry(f, num_planes, &g)) return fail(ctx, TF_GPU_ERR_INVALID, "bad frame geometry");
+  DevFrame *d = find_cached(ctx, f->frame_id, &g);
+  if (!d) {
+    DevFrame *victim = nullptr;
+    for (auto &s : ctx->cache) {
+      if (s.pinned_epoch == ctx->epoch) continue;
+      if (!s.valid) {
+        victim = &s;
+        break;
+      }
+      if (!victim || s.last_use < victim->last_use) victim = &s;
+    }
+    if (!victim) return fail(ctx, TF_GPU_ERR_MEM, "frame cache too small for this window");
+    int rc = alloc_dev_frame(ctx, victim, g);
+    if (rc) return rc;
+    victim->valid = false;
+    rc = upload_frame(ctx, victim, f);
+    if (rc) return rc;
+    d = victim;
+  }
+  d->last_use = ++ctx->use_counter;
+  d->pinned_epoch = ctx->epoch;
+  *out = d;
+  return TF_GPU_OK;
+}
+
+int validate_params(tf_gpu_ctx *ctx, const tf_gpu_params *p) {
+  if (!p) return fail(ctx, TF_GPU_ERR_INVALID, "params is NULL");
+  if (p->num_frames < 1 || p->num_frames > TF_GPU_MAX_FRAMES) return fail(ctx, TF_GPU_ERR_INVALID, "num_frames %d out of [1,%d]", p->num_frames, TF_GPU_MAX_FRAMES);
+  if (p->filter_frame_idx < 0 || p->filter_frame_idx >= p->num_frames) return fail(ctx, TF_GPU_ERR_INVALID, "filter_frame_idx out of range");
+  if (p->num_planes != 1 && p->num_planes != 3) return fail(ctx, TF_GPU_ERR_INVALID, "num_planes must be 1 or 3");
+  if (p->bit_depth != 8 && p->bit_depth != 10 && p->bit_depth != 12) return fail(ctx, TF_GPU_ERR_INVALID, "bit_depth must be 8, 10 or 12");
+  if (p->subpel_method < 0 || p->subpel_method > 2) return fail(ctx, TF_GPU_ERR_INVALID, "bad subpel_method");
+  if (p->filter_strength < 0 || p->filter_strength > 6) return fail(ctx, TF_GPU_ERR_INVALID, "filter_strength out of [0,6]");
+  if (p->q_factor < 0 || p->q_factor > 255 * 8) return fail(ctx, TF_GPU_ERR_INVALID, "q_factor out of range");
+  return TF_GPU_OK;
+}
+
+void build_sites(Sites *s) {  // av1_init_motion_compensation_nstep (mcomp.c:433-475), level 0
+  memset(s, 0, sizeof(*s));
+  int radius = 1;
+  for (int st = 0; st < 15; st++) {
+    int tan_radius = (int)(0.41 * radius);
+    if (tan_radius < 1) tan_radius = 1;
+    int n = 12;
+    if (radius <= 5) {
+      tan_radius = radius;
+      n = 8;
+    }
+    const int m[13][2] = { { 0, 0 },
+                           { -radius, 0 },
+                           { radius, 0 },
+                           { 0, -radius },
+                           { 0, radius },
+                           { -radius, -tan_radius },
+                           { radius, tan_radius },
+                           { -tan_radius, radius },
+                           { tan_radius, -radius },
+                           { -radius, tan_radius },
+                           { radius, -tan_radius },
+                           { tan_radius, radius },
+                           { -tan_radius, -radius } };
+    for (int i = 0; i <= n; i++) {
+      s->r[st][i] = (int16_t)m[i][0];
+      s->c[st][i] = (int16_t)m[i][1];
+    }
+    s->n[st] = n;
+    s->radius[st] = radius;
+    if (st < 12) {
+      const double a = radius * 1.5 + 0.5;
+      radius = (int)(a > radius + 1 ? a : radius + 1);
+    }
+  }
+}
+
+const int16_t K12[16][12] = {  // av1_sub_pel_filters_12sharp, av1/common/filter.h:159-177
+  { 0, 0, 0, 0, 0, 128, 0, 0, 0, 0, 0, 0 },         { 0, 1, -2, 3, -7, 127, 8, -4, 2, -1, 1, 0 },
+  { -1, 2, -3, 6, -13, 124, 18, -8, 4, -2, 2, -1 }, { -1, 3, -4, 8, -18, 120, 28, -12, 7, -4, 2, -1 },
+  { -1, 3, -6, 10, -21, 115, 38, -15, 8, -5, 3, -1 }, { -2, 4, -6, 12, -24, 108, 49, -18, 10, -6, 3, -2 },
+  { -2, 4, -7, 13, -25, 100, 60, -21, 11, -7, 4, -2 }, { -2, 4, -7, 13, -26, 91, 71, -24, 13, -7, 4, -2 },
+  { -2, 4, -7, 13, -25, 81, 81, -25, 13, -7, 4, -2 }, { -2, 4, -7, 13, -24, 71, 91, -26, 13, -7, 4, -2 },
+  { -2, 4, -7, 11, -21, 60, 100, -25, 13, -7, 4, -2 }, { -2, 3, -6, 10, -18, 49, 108, -24, 12, -6, 4, -2 },
+  { -1, 3, -5, 8, -15, 38, 115, -21, 10, -6, 3, -1 }, { -1, 2, -4, 7, -12, 28, 120, -18, 8, -4, 3, -1 },
+  { -1, 2, -2, 4, -8, 18, 124, -13, 6, -3, 2, -1 },  { 0, 1, -1, 2, -4, 8, 127, -7, 3, -2, 1, 0 }
+};
+const int16_t K8[16][8] = {  // av1_sub_pel_filters_8, av1/common/filter.h:123-133
+  { 0, 0, 0, 128, 0, 0, 0, 0 },      { 0, 2, -6, 126, 8, -2, 0, 0 },    { 0, 2, -10, 122, 18, -4, 0, 0 },
+  { 0, 2, -12, 116, 28, -8, 2, 0 },  { 0, 2, -14, 110, 38, -10, 2, 0 }, { 0, 2, -14, 102, 48, -12, 2, 0 },
+  { 0, 2, -16, 94, 58, -12, 2, 0 },  { 0, 2, -14, 84, 66, -12, 2, 0 },  { 0, 2, -14, 76, 76, -14, 2, 0 },
+  { 0, 2, -12, 66, 84, -14, 2, 0 },  { 0, 2, -12, 58, 94, -16, 2, 0 },  { 0, 2, -12, 48, 102, -14, 2, 0 },
+  { 0, 2, -10, 38, 110, -14, 2, 0 }, { 0, 2, -8, 28, 116, -12, 2, 0 },  { 0, 0, -4, 18, 122, -10, 2, 0 },
+  { 0, 0, -2, 8, 126, -6, 2, 0 }
+};
+
+int ensure_dump(tf_gpu_ctx *ctx, int i, size_t bytes) {
+  if (ctx->d_dump_sz[i] >= bytes) return TF_GPU_OK;
+  if (ctx->d_dump[i]) cudaFree(ctx->d_dump[i]);
+  ctx->d_dump[i] = nullptr;
+  ctx->d_dump_sz[i] = 0;
+  CU(cudaMalloc(&ctx->d_dump[i], bytes));
+  ctx->d_dump_sz[i] = bytes;
+  return TF_GPU_OK;
+}
+
+// Build kernel parameters and launch the block kernel over rows [rb, re).
+int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *frames, const Geometry &g,
+                  unsigned long long *d_diff, const tf_gpu_dump *dump, bool timed) {
+  KParams K;
+  memset(&K, 0, sizeof(K));
+  K.width = g.crop_w[0];
+  K.height = g.crop_h[0];
+  K.mb_rows = (K.height + 31) / 32;  // get_num_blocks, temporal_filter.c:1236-1237
+  K.mb_cols = (K.width + 31) / 32;
+  K.mi_rows = p->mi_rows;
+  K.mi_cols = p->mi_cols;
+  K.ss_x = g.ss_x;
+  K.ss_y = g.ss_y;
+  K.num_planes = p->num_planes;
+  K.bit_depth = p->bit_depth;
+  K.is_hbd = g.is_hbd;
+  for (int k = 0; k < 2; k++) {
+    K.aligned_w[k] = g.aligned_w[k];
+    K.aligned_h[k] = g.aligned_h[k];
+    K.pitch[k] = g.pitch[k];
+    K.out_pitch[k] = ctx->out.g.pitch[k];
+  }
+  K.border = p->border_in_pixels;
+  K.num_frames = p->num_frames;
+  K.filter_idx = p->filter_frame_idx;
+  K.q_factor = p->q_factor;
+  K.strength = p->filter_strength;
+  K.force_integer_mv = p->force_integer_mv;
+  K.allow_hp = p->allow_hp;
+  K.subpel_method = p->subpel_method;
+  K.iters_per_step = p->subpel_iters_per_step;
+  K.prune_level = p->prune_mesh_level;
+  for (int i = 0; i < 4; i++) {
+    K.mesh[i][0] = p->mesh_patterns[i][0];
+    K.mesh[i][1] = p->mesh_patterns[i][1];
+  }
+  K.use_skip = p->use_downsampled_sad ? 1 : 0;
+  K.compute_diff = p->compute_frame_diff ? 1 : 0;
+  const int min_frame_size = K.width < K.height ? K.width : K.height;
+  // MV_COST_L1_{LOW,MID,HD}RES (temporal_filter.c:119-122, mcomp.c:237-244)
+  if (min_frame_size >= 720) { K.sad_lambda = 8; K.sse_lambda = 1; }
+  else if (min_frame_size >= 480) { K.sad_lambda = 15; K.sse_lambda = 0; }
+  else { K.sad_lambda = 32; K.sse_lambda = 2; }
+  {  // av1_init_search_range (mcomp.c:217-226)
+    int size = K.width > K.height ? K.width : K.height;
+    if (size < 16) size = 16;
+    int sr = 0;
+    while ((size << sr) < 1023) sr++;
+    K.step_param = sr < 9 ? sr : 9;
+  }
+  K.mse_thresh = ((min_frame_size >= 720) ? 12 : 3) << (p->bit_depth - 8);  // temporal_filter.c:249-250
+  K.hbd_shift = g.is_hbd ? (p->bit_depth == 10 ? 2 : (p->bit_depth == 12 ? 4 : 0)) : 0;
+  {  // decay factors, temporal_filter.c:583-597 (host libm, as the reference)
+    double q_decay = pow((double)p->q_factor / 20, 2);
+    q_decay = q_decay < 1e-5 ? 1e-5 : (q_decay > 1 ? 1 : q_decay);
+    if (p->q_factor >= 128) q_decay = 0.5 * pow((double)p->q_factor / 64, 2);
+    double s_decay = pow((double)p->filter_strength / 4, 2);
+    s_decay = s_decay < 1e-5 ? 1e-5 : (s_decay > 1 ? 1 : s_decay);
+    for (int pl = 0; pl < p->num_planes; pl++) {
+      const double n_decay = 0.5 + log(2 * p->noise_levels[pl] + 5.0);
+      K.decay[pl] = 1 / (n_decay * q_decay * s_decay);
+    }
+    double thr = min_frame_size * 0.1;  // TF_SEARCH_DISTANCE_THRESHOLD, :603-604
+    K.dist_thr = thr > 1 ? thr : 1;
+  }
+  for (int f = 0; f < p->num_frames; f++)
+    for (int pl = 0; pl < p->num_planes; pl++) K.frm[f][pl] = frames[f]->p00[pl];
+  for (int pl = 0; pl < p->num_planes; pl++) K.out[pl] = ctx->out.p00[pl];
+  K.diff = d_diff;
+  K.num_pels = 1024 + (p->num_planes > 1 ? 2 * (1024 >> (g.ss_x + g.ss_y)) : 0);
+  K.row_begin = 0;
+  K.row_end = K.mb_rows;
+  if (p->out_row_end > p->out_row_begin) {
+    K.row_begin = p->out_row_begin < 0 ? 0 : p->out_row_begin;
+    K.row_end = p->out_row_end > K.mb_rows ? K.mb_rows : p->out_row_end;
+  }
+  const int nblocks_all = K.mb_rows * K.mb_cols;
+  if (dump) {
+    const size_t bf = (size_t)nblocks_all * p->num_frames;
+    int rc = 0;
+    if (dump->subblock_mvs) { rc = ensure_dump(ctx, 0, bf * 8 * sizeof(int16_t)); if (rc) return rc; K.d_mvs = (int16_t *)ctx->d_dump[0]; cudaMemsetAsync(K.d_mvs, 0, bf * 8 * sizeof(int16_t), ctx->stream); }
+    if (dump->subblock_mses) { rc = ensure_dump(ctx, 1, bf * 4 * sizeof(int32_t)); if (rc) return rc; K.d_mses = (int32_t *)ctx->d_dump[1]; cudaMemsetAsync(K.d_mses, 0, bf * 4 * sizeof(int32_t), ctx->stream); }
+    if (dump->pred) { rc = ensure_dump(ctx, 2, bf * K.num_pels * sizeof(uint16_t)); if (rc) return rc; K.d_pred = (uint16_t *)ctx->d_dump[2]; cudaMemsetAsync(K.d_pred, 0, bf * K.num_pels * sizeof(uint16_t), ctx->stream); }
+    if (dump->accum) { rc = ensure_dump(ctx, 3, (size_t)nblocks_all * K.num_pels * sizeof(uint32_t)); if (rc) return rc; K.d_accum = (uint32_t *)ctx->d_dump[3]; }
+    if (dump->count) { rc = ensure_dump(ctx, 4, (size_t)nblocks_all * K.num_pels * sizeof(uint16_t)); if (rc) return rc; K.d_count = (uint16_t *)ctx->d_dump[4]; }
+  }
+  const int grid = (K.row_end - K.row_begin) * K.mb_cols;
+  if (grid <= 0) return fail(ctx, TF_GPU_ERR_INVALID, "empty row range");
+  const size_t smem = warp_smem_bytes(K.num_pels);
+  if (timed) CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (g.is_hbd)
+    tf_block_kernel<uint16_t><<<grid, 32, smem, ctx->stream>>>(K);
+  else
+    tf_block_kernel<uint8_t><<<grid, 32, smem, ctx->stream>>>(K);
+  CU(cudaGetLastError());
+  if (timed) CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->last_launches++;
+  return TF_GPU_OK;
+}
+
+int download_dump(tf_gpu_ctx *ctx, const tf_gpu_params *p, const Geometry &g, const tf_gpu_dump *dump) {
+  const int mb_rows = (g.crop_h[0] + 31) / 32, mb_cols = (g.crop_w[0] + 31) / 32;
+  const size_t nb = (size_t)mb_rows * mb_cols, bf = nb * p->num_frames;
+  const int num_pels = 1024 + (p->num_planes > 1 ? 2 * (1024 >> (g.ss_x + g.ss_y)) : 0);
+  if (dump->subblock_mvs) CU(cudaMemcpyAsync(dump->subblock_mvs, ctx->d_dump[0], bf * 8 * sizeof(int16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dump->subblock_mses) CU(cudaMemcpyAsync(dump->subblock_mses, ctx->d_dump[1], bf * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dump->pred) CU(cudaMemcpyAsync(dump->pred, ctx->d_dump[2], bf * num_pels * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dump->accum) CU(cudaMemcpyAsync(dump->accum, ctx->d_dump[3], nb * num_pels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dump->count) CU(cudaMemcpyAsync(dump->count, ctx->d_dump[4], nb * num_pels * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  return TF_GPU_OK;
+}
+
+// Copy block rows [rb, re) of the device output into the caller's planes.
+int download_rows(tf_gpu_ctx *ctx, tf_gpu_frame *out, int rb, int re) {
+  const Geometry &g = ctx->out.g;
+  const size_t es = g.is_hbd ? 2 : 1;
+  const int mb_cols = (g.crop_w[0] + 31) / 32;
+  for (int pl = 0; pl < g.num_planes; pl++) {
+    const int k = pl > 0;
+    const int bh = 32 >> (pl ? g.ss_y : 0), bw = 32 >> (pl ? g.ss_x : 0);
+    if (!out->plane[pl]) return fail(ctx, TF_GPU_ERR_INVALID, "output plane %d is NULL", pl);
+    // full blocks, as temporal_filter.c:740-777 writes them, but never beyond the
+    // host allocation (aligned size + host border)
+    int cols = mb_cols * bw, y0 = rb * bh, y1 = re * bh;
+    const int max_cols = out->aligned_w[k] + (k ? out->border >> g.ss_x : out->border);
+    const int max_rows = out->aligned_h[k] + (k ? out->border >> g.ss_y : out->border);
+    if (cols > max_cols) cols = max_cols;
+    if (cols > out->stride[k]) cols = out->stride[k];
+    if (y1 > max_rows) y1 = max_rows;
+    if (y1 <= y0) continue;
+    char *dst = (char *)out->plane[pl] + (size_t)y0 * out->stride[k] * es;
+    const char *src = (const char *)ctx->out.p00[pl] + (size_t)y0 * g.pitch[k] * es;
+    CU(cudaMemcpy2DAsync(dst, (size_t)out->stride[k] * es, src, (size_t)g.pitch[k] * es, (size_t)cols * es, y1 - y0,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return TF_GPU_OK;
+}
+
+int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame *frames, tf_gpu_frame *out,
+                int64_t diff_sum_sse[2], const tf_gpu_dump *dump, uint64_t *ticket_out) {
+  if (!ctx) return TF_GPU_ERR_INVALID;
+  int rc = validate_params(ctx, params);
+  if (rc) return rc;
+  if (!frames || !out) return fail(ctx, TF_GPU_ERR_INVALID, "frames/out is NULL");
+  CU(cudaSetDevice(ctx->device));
+  if ((int)ctx->cache.size() < params->num_frames) return fail(ctx, TF_GPU_ERR_MEM, "frame cache smaller than the window");
+  ctx->epoch++;
+  ctx->last_launches = 0;
+  DevFrame *devf[TF_GPU_MAX_FRAMES];
+  for (int i = 0; i < params->num_frames; i++) {
+    if (frames[i].is_hbd != frames[0].is_hbd) return fail(ctx, TF_GPU_ERR_INVALID, "mixed bit depth containers");
+    rc = get_frame(ctx, &frames[i], params->num_planes, &devf[i]);
+    if (rc) return rc;
+    if (!(devf[i]->g == devf[0]->g)) return fail(ctx, TF_GPU_ERR_INVALID, "frames of one window must share geometry");
+  }
+  const Geometry &g = devf[0]->g;
+  if (g.is_hbd == 0 && params->bit_depth != 8) return fail(ctx, TF_GPU_ERR_INVALID, "8-bit container needs bit_depth 8");
+  rc = alloc_dev_frame(ctx, &ctx->out, g);
+  if (rc) return rc;
+  Ticket &t = ctx->tickets[ctx->next_ticket % 8];
+  if (t.pending) return fail(ctx, TF_GPU_ERR_INVALID, "too many submits in flight (max 8)");
+  const int slot = (int)(ctx->next_ticket % 8);
+  unsigned long long *d_diff = ctx->d_diff + 2 * slot;
+  CU(cudaMemsetAsync(d_diff, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  rc = launch_filter(ctx, params, devf, g, d_diff, dump, true);
+  if (rc) return rc;
+  const int mb_rows = (g.crop_h[0] + 31) / 32;
+  int rb = 0, re = mb_rows;
+  if (params->out_row_end > params->out_row_begin) {
+    rb = params->out_row_begin < 0 ? 0 : params->out_row_begin;
+    re = params->out_row_end > mb_rows ? mb_rows : params->out_row_end;
+  }
+  rc = download_rows(ctx, out, rb, re);
+  if (rc) return rc;
+  if (dump) {
+    rc = download_dump(ctx, params, g, dump);
+    if (rc) return rc;
+  }
+  CU(cudaMemcpyAsync(ctx->h_diff + 2 * slot, d_diff, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(t.ev, ctx->stream));
+  t.id = ctx->next_ticket++;
+  t.diff_dst = diff_sum_sse;
+  t.want_diff = diff_sum_sse != nullptr;
+  t.pending = true;
+  *ticket_out = t.id;
+  return TF_GPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tf_gpu_abi_version(void) { return TF_GPU_ABI_VERSION; }
+
+int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
+  if (!out) return TF_GPU_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return TF_GPU_ERR_NO_DEVICE;
+  tf_gpu_ctx *ctx = new (std::nothrow) tf_gpu_ctx();
+  if (!ctx) return TF_GPU_ERR_MEM;
+  int dev = cfg ? cfg->device : -1;
+  if (dev < 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  }
+  if (dev >= ndev) {
+    delete ctx;
+    return TF_GPU_ERR_NO_DEVICE;
+  }
+  ctx->device = dev;
+  int slots = (cfg && cfg->max_cached_frames > 0) ? cfg->max_cached_frames : 32;
+  if (slots < TF_GPU_MAX_FRAMES) slots = TF_GPU_MAX_FRAMES;
+  ctx->cache.resize(slots);
+  cudaError_t e = cudaSetDevice(dev);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->tickets[i].ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_diff, 16 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_diff, 16 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_noise, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_noise, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) {
+    Sites s;
+    build_sites(&s);
+    e = cudaMemcpyToSymbol(c_sites, &s, sizeof(s));
+  }
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_k12, K12, sizeof(K12));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_k8, K8, sizeof(K8));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tf_block_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(3072));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tf_block_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(3072));
+  if (e != cudaSuccess) {
+    tf_gpu_destroy(ctx);
+    return e == cudaErrorMemoryAllocation ? TF_GPU_ERR_MEM : TF_GPU_ERR_CUDA;
+  }
+  *out = ctx;
+  return TF_GPU_OK;
+}
+
+void tf_gpu_destroy(tf_gpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto &d : ctx->cache)
+    for (int p = 0; p < 3; p++)
+      if (d.base[p]) cudaFree(d.base[p]);
+  for (int p = 0; p < 3; p++)
+    if (ctx->out.base[p]) cudaFree(ctx->out.base[p]);
+  for (int i = 0; i < 5; i++)
+    if (ctx->d_dump[i]) cudaFree(ctx->d_dump[i]);
+  if (ctx->d_diff) cudaFree(ctx->d_diff);
+  if (ctx->h_diff) cudaFreeHost(ctx->h_diff);
+  if (ctx->d_noise) cudaFree(ctx->d_noise);
+  if (ctx->h_noise) cudaFreeHost(ctx->h_noise);
+  for (int i = 0; i < 8; i++)
+    if (ctx->tickets[i].ev) cudaEventDestroy(ctx->tickets[i].ev);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *tf_gpu_last_error(const tf_gpu_ctx *ctx) { return ctx ? ctx->err : "no context (no CUDA device?)"; }
+
+int tf_gpu_cache_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *frame) {
+  if (!ctx || !frame) return TF_GPU_ERR_INVALID;
+  if (!frame->frame_id) return fail(ctx, TF_GPU_ERR_INVALID, "frame_id 0 cannot be cached");
+  CU(cudaSetDevice(ctx->device));
+  ctx->epoch++;
+  DevFrame *d;
+  const int num_planes = frame->plane[1] ? 3 : 1;
+  int rc = get_frame(ctx, frame, num_planes, &d);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_evict_frame(tf_gpu_ctx *ctx, uint64_t frame_id) {
+  if (!ctx) return TF_GPU_ERR_INVALID;
+  for (auto &d : ctx->cache)
+    if (d.valid && d.frame_id == frame_id) d.valid = false;
+  return TF_GPU_OK;
+}
+
+int tf_gpu_estimate_noise(tf_gpu_ctx *ctx, const tf_gpu_frame *frame, int plane, int bit_depth, int edge_thresh,
+                          double *noise_level) {
+  if (!ctx || !frame || !noise_level) return TF_GPU_ERR_INVALID;
+  if (plane < 0 || plane > 2) return fail(ctx, TF_GPU_ERR_INVALID, "plane out of range");
+  CU(cudaSetDevice(ctx->device));
+  ctx->epoch++;
+  ctx->last_launches = 0;
+  DevFrame *d;
+  const int num_planes = frame->plane[1] ? 3 : 1;
+  if (plane >= num_planes) return fail(ctx, TF_GPU_ERR_INVALID, "plane not present");
+  int rc = get_frame(ctx, frame, num_planes, &d);
+  if (rc) return rc;
+  const Geometry &g = d->g;
+  const int k = plane > 0;
+  const int w = g.crop_w[k], h = g.crop_h[k];
+  CU(cudaMemsetAsync(ctx->d_noise, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  if (w > 2 && h > 2) {
+    const long long n = (long long)(w - 2) * (h - 2);
+    const int threads = 256;
+    long long blocks = (n + threads - 1) / threads;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (g.is_hbd)
+      noise_kernel<uint16_t><<<(int)blocks, threads, 0, ctx->stream>>>((const uint16_t *)d->p00[plane], g.pitch[k], w, h, bit_depth, edge_thresh, ctx->d_noise);
+    else
+      noise_kernel<uint8_t><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)d->p00[plane], g.pitch[k], w, h, bit_depth, edge_thresh, ctx->d_noise);
+    CU(cudaGetLastError());
+    ctx->last_launches++;
+  }
+  CU(cudaMemcpyAsync(ctx->h_noise, ctx->d_noise, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const long long accum = (long long)ctx->h_noise[0];
+  const int count = (int)ctx->h_noise[1];
+  // temporal_filter.c:1193, SQRT_PI_BY_2 :1148
+  *noise_level = (count < 16) ? -1.0 : (double)accum / (6 * count) * 1.25331413732;
+  return TF_GPU_OK;
+}
+
+int tf_gpu_submit(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame *frames, tf_gpu_frame *out,
+                  int64_t diff_sum_sse[2], uint64_t *ticket) {
+  if (!ticket) return TF_GPU_ERR_INVALID;
+  return submit_impl(ctx, params, frames, out, diff_sum_sse, nullptr, ticket);
+}
+
+int tf_gpu_wait(tf_gpu_ctx *ctx, uint64_t ticket) {
+  if (!ctx) return TF_GPU_ERR_INVALID;
+  Ticket &t = ctx->tickets[ticket % 8];
+  if (!t.pending || t.id != ticket) return fail(ctx, TF_GPU_ERR_INVALID, "unknown ticket");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(t.ev));
+  t.pending = false;
+  if (t.want_diff) {
+    t.diff_dst[0] = (int64_t)ctx->h_diff[2 * (ticket % 8)];
+    t.diff_dst[1] = (int64_t)ctx->h_diff[2 * (ticket % 8) + 1];
+  }
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_kernel_ms = ms;
+  return TF_GPU_OK;
+}
+
+int tf_gpu_filter_dump(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame *frames, tf_gpu_frame *out,
+                       int64_t diff_sum_sse[2], const tf_gpu_dump *dump) {
+  uint64_t t;
+  int rc = submit_impl(ctx, params, frames, out, diff_sum_sse, dump, &t);
+  if (rc) return rc;
+  return tf_gpu_wait(ctx, t);
+}
+
+int tf_gpu_filter(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame *frames, tf_gpu_frame *out,
+                  int64_t diff_sum_sse[2]) {
+  return tf_gpu_filter_dump(ctx, params, frames, out, diff_sum_sse, nullptr);
+}
+
+int tf_gpu_filter_resident(tf_gpu_ctx *ctx, const tf_gpu_params *params, const uint64_t *frame_ids,
+                           int64_t diff_sum_sse[2], float *time_ms) {
+  if (!ctx || !frame_ids) return TF_GPU_ERR_INVALID;
+  int rc = validate_params(ctx, params);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  ctx->epoch++;
+  ctx->last_launches = 0;
+  DevFrame *devf[TF_GPU_MAX_FRAMES];
+  for (int i = 0; i < params->num_frames; i++) {
+    devf[i] = find_cached(ctx, frame_ids[i], nullptr);
+    if (!devf[i]) return fail(ctx, TF_GPU_ERR_INVALID, "frame id %llu is not resident", (unsigned long long)frame_ids[i]);
+    if (!(devf[i]->g == devf[0]->g)) return fail(ctx, TF_GPU_ERR_INVALID, "frames of one window must share geometry");
+    devf[i]->last_use = ++ctx->use_counter;
+    devf[i]->pinned_epoch = ctx->epoch;
+  }
+  const Geometry &g = devf[0]->g;
+  if (g.num_planes < params->num_planes) return fail(ctx, TF_GPU_ERR_INVALID, "resident frames lack chroma planes");
+  rc = alloc_dev_frame(ctx, &ctx->out, g);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(ctx->d_diff, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  rc = launch_filter(ctx, params, devf, g, ctx->d_diff, nullptr, true);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->h_diff, ctx->d_diff, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (diff_sum_sse) {
+    diff_sum_sse[0] = (int64_t)ctx->h_diff[0];
+    diff_sum_sse[1] = (int64_t)ctx->h_diff[1];
+  }
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_kernel_ms = ms;
+  if (time_ms) *time_ms = ms;
+  return TF_GPU_OK;
+}
+
+int tf_gpu_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, int row_begin, int row_end) {
+  if (!ctx || !out) return TF_GPU_ERR_INVALID;
+  if (!ctx->out.base[0]) return fail(ctx, TF_GPU_ERR_INVALID, "no output on the device yet");
+  CU(cudaSetDevice(ctx->device));
+  const int mb_rows = (ctx->out.g.crop_h[0] + 31) / 32;
+  if (row_end <= row_begin) {
+    row_begin = 0;
+    row_end = mb_rows;
+  }
+  if (row_begin < 0) row_begin = 0;
+  if (row_end > mb_rows) row_end = mb_rows;
+  int rc = download_rows(ctx, out, row_begin, row_end);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_output_device_plane(tf_gpu_ctx *ctx, int plane, void **dptr, size_t *pitch_bytes, int *rows,
+                               int *row_bytes) {
+  if (!ctx || plane < 0 || plane > 2 || !ctx->out.p00[plane]) return TF_GPU_ERR_INVALID;
+  const Geometry &g = ctx->out.g;
+  const int k = plane > 0;
+  const size_t es = g.is_hbd ? 2 : 1;
+  if (dptr) *dptr = ctx->out.p00[plane];
+  if (pitch_bytes) *pitch_bytes = (size_t)g.pitch[k] * es;
+  if (rows) *rows = ((g.crop_h[0] + 31) / 32) * (32 >> (plane ? g.ss_y : 0));
+  if (row_bytes) *row_bytes = (int)(((g.crop_w[0] + 31) / 32) * (32 >> (plane ? g.ss_x : 0)) * es);
+  return TF_GPU_OK;
+}
+
+int tf_gpu_host_register(tf_gpu_ctx *ctx, void *ptr, size_t bytes) {
+  if (!ctx || !ptr) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_host_unregister(tf_gpu_ctx *ctx, void *ptr) {
+  if (!ctx || !ptr) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaHostUnregister(ptr));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_last_stats(const tf_gpu_ctx *ctx, int *kernel_launches, float *filter_kernel_ms) {
+  if (!ctx) return TF_GPU_ERR_INVALID;
+  if (kernel_launches) *kernel_launches = ctx->last_launches;
+  if (filter_kernel_ms) *filter_kernel_ms = ctx->last_kernel_ms;
+  return TF_GPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1135 @@
+// Device code of the B200 temporal filter.  Hand-written CUDA for sm_100a.
+//
+// One warp owns one 32x32 block of the frame to filter and walks the whole
+// window frame by frame (the reference chains ref_mv from frame to frame,
+// av1/encoder/temporal_filter.c:855-871, so the frame loop is sequential per
+// block while the 2,040 / 8,160 blocks of a 1080p / 4K frame are independent).
+// Motion search, predictor, weights, accumulate/count, normalisation and the
+// FRAME_DIFF reduction are fused: pred / accum / count never leave shared
+// memory.  Every data-dependent decision of the reference's search is replayed
+// warp-uniformly (all lanes take the same branch after a shuffle reduction), so
+// motion vectors are bit-exact by construction.
+//
+// Integer work is byte/halfword SIMD-in-word: VABSDIFF4.U8.ACC (__vsadu4) for
+// 8-bit SAD, VIMNMX.U16x2 (max-min) for high-bitdepth SAD, IDP.4A for
+// sum/sum-of-squares.  No tensor cores: nothing on this path is a dense
+// contraction.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tfk {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAXF = 24;
+constexpr int INT_MAX_ = 0x7fffffff;
+
+// NSTEP site table (mcomp.c:433-475), built on the host.
+struct Sites {
+  int16_t r[15][13];
+  int16_t c[15][13];
+  int32_t n[15];
+  int32_t radius[15];
+};
+__constant__ Sites c_sites;
+// MULTITAP_SHARP2 12-tap kernels (av1/common/filter.h:159-177) and
+// EIGHTTAP_REGULAR (filter.h:123-133) -- numeric tables of the AV1 format.
+__constant__ int16_t c_k12[16][12];
+__constant__ int16_t c_k8[16][8];
+
+struct KParams {
+  // geometry
+  int width, height;  // luma crop
+  int mb_rows, mb_cols, mi_rows, mi_cols;
+  int ss_x, ss_y, num_planes, bit_depth, is_hbd;
+  int aligned_w[2], aligned_h[2];
+  int border;  // oxcf.border_in_pixels
+  int num_frames, filter_idx;
+  int q_factor, strength;
+  int force_integer_mv, allow_hp, subpel_method, iters_per_step;
+  int prune_level, mesh[4][2], use_skip, compute_diff;
+  int sad_lambda, sse_lambda, step_param, mse_thresh;
+  int hbd_shift;  // 0, 2 (10 bit), 4 (12 bit): SAD >>, variance rounding
+  int row_begin, row_end;
+  double decay[3];
+  double dist_thr;  // max(min(w,h) * 0.1, 1)
+  // planes (pointers to pixel (0,0)); pitch in samples
+  const void *frm[MAXF][3];
+  int pitch[2];
+  void *out[3];
+  int out_pitch[2];
+  unsigned long long *diff;  // [2]
+  // optional dumps (device)
+  int16_t *d_mvs;
+  int32_t *d_mses;
+  uint16_t *d_pred;
+  uint32_t *d_accum;
+  uint16_t *d_count;
+  int num_pels;
+};
+
+struct MV2 {
+  int row, col;
+};
+struct Lim {
+  int col_min, col_max, row_min, row_max;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int iabs(int x) { return x < 0 ? -x : x; }
+__device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
+__device__ __forceinline__ int iclamp(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int rpot(int v, int n) { return (v + ((1 << n) >> 1)) >> n; }
+
+template <int N>
+__device__ __forceinline__ unsigned seg_reduce_u32(unsigned v) {
+#pragma unroll
+  for (int o = N / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i32(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// Search context (warp-uniform)
+// ---------------------------------------------------------------------------
+template <typename T>
+struct Search {
+  const T *src;  // block origin in the frame to filter
+  const T *ref;  // co-located origin in the reference frame
+  int stride;    // samples
+  Lim lim;       // full-pel limits
+  int sad_lambda, sse_lambda;
+  int hbd_shift;
+  int is_hbd;
+};
+
+// SAD lane layout: a candidate occupies LPC lanes (one block row per lane, every
+// other row with skip-row SAD, aom_dsp/sad.c:66-70), so a pass evaluates
+// CPP = 32 / LPC candidates at once.
+template <typename T, int W, bool SKIP>
+struct SadL {
+  static constexpr int ROWS = SKIP ? W / 2 : W;
+  static constexpr int LPC = ROWS;
+  static constexpr int CPP = 32 / LPC;
+  static constexpr int NW = W * (int)sizeof(T) / 4;
+  static constexpr int RSTEP = SKIP ? 2 : 1;
+};
+
+template <typename T, int W, bool SKIP>
+__device__ __forceinline__ void sad_load_src(const T *src, int stride, uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+  using L = SadL<T, W, SKIP>;
+  const int row = (lane_id() % L::LPC) * L::RSTEP;
+  const uint4 *p = reinterpret_cast<const uint4 *>(src + row * stride);
+#pragma unroll
+  for (int j = 0; j < L::NW / 4; j++) {
+    const uint4 v = __ldg(p + j);
+    sw[4 * j + 0] = v.x;
+    sw[4 * j + 1] = v.y;
+    sw[4 * j + 2] = v.z;
+    sw[4 * j + 3] = v.w;
+  }
+}
+
+// Partial SAD of this lane's row of the candidate at full-pel (r, c).
+template <typename T, int W, bool SKIP>
+__device__ __forceinline__ unsigned sad_partial(const T *ref, int stride, int r, int c, bool valid,
+                                                const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+  using L = SadL<T, W, SKIP>;
+  if (!valid) return 0u;
+  const int row = (lane_id() % L::LPC) * L::RSTEP;
+  const T *p = ref + (r + row) * stride + c;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+  const unsigned sh = (unsigned)(a & 3) * 8;
+  uint32_t w[L::NW + 1];
+#pragma unroll
+  for (int j = 0; j <= L::NW; j++) w[j] = __ldg(wp + j);
+  unsigned s = 0;
+  if (sizeof(T) == 1) {
+#pragma unroll
+    for (int j = 0; j < L::NW; j++) s = __vsadu4(__funnelshift_r(w[j], w[j + 1], sh), sw[j]) + s;
+  } else {
+    unsigned acc = 0;  // two u16 lanes; NW <= 16 words of <= 4095 each: no carry
+#pragma unroll
+    for (int j = 0; j < L::NW; j++) {
+      const unsigned x = __funnelshift_r(w[j], w[j + 1], sh);
+      acc += __vmaxu2(x, sw[j]) - __vminu2(x, sw[j]);
+    }
+    s = (acc & 0xffffu) + (acc >> 16);
+  }
+  return s;
+}
+
+// mvsad_err_cost (mcomp.c:310-331), L1, ref = 0
+template <typename T>
+__device__ __forceinline__ int sad_cost(const Search<T> &S, int r, int c) {
+  return (S.sad_lambda * (iabs(r * 8) + iabs(c * 8))) >> 3;
+}
+// mv_err_cost (mcomp.c:271-295) on a 1/8-pel mv
+template <typename T>
+__device__ __forceinline__ int sse_cost(const Search<T> &S, int r8, int c8) {
+  return (S.sse_lambda * (iabs(r8) + iabs(c8))) >> 3;
+}
+__device__ __forceinline__ bool in_range(const Lim &l, int r, int c) {
+  return c >= l.col_min && c <= l.col_max && r >= l.row_min && r <= l.row_max;
+}
+template <bool SKIP>
+__device__ __forceinline__ unsigned sad_post(unsigned s, int hbd_shift) {
+  if (SKIP) s *= 2;
+  return s >> hbd_shift;
+}
+
+// SAD of one candidate, result in all lanes.
+template <typename T, int W, bool SKIP>
+__device__ __forceinline__ unsigned sad_single(const Search<T> &S, int r, int c,
+                                               const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+  using L = SadL<T, W, SKIP>;
+  unsigned part = sad_partial<T, W, SKIP>(S.ref, S.stride, r, c, lane_id() < L::LPC, sw);
+  part = seg_reduce_u32<L::LPC>(part);
+  part = __shfl_sync(FULL, part, 0);
+  return sad_post<SKIP>(part, S.hbd_shift);
+}
+
+// ---------------------------------------------------------------------------
+// Variance (aom_dsp/variance.c:56-72,141-148; hbd :342-429).  a - b, W x W.
+// Lane = column (W == 32) or (row half, column) (W == 16).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned var_finish(int sum, unsigned long long sse, int W, int hbd_shift,
+                                               unsigned *sse_out) {
+  if (hbd_shift == 0) {
+    const unsigned sse32 = (unsigned)sse;
+    *sse_out = sse32;
+    return sse32 - (unsigned)(((long long)sum * sum) / (W * W));
+  }
+  const int sh = hbd_shift;
+  const unsigned sse32 = (unsigned)((sse + ((1ull << (2 * sh)) >> 1)) >> (2 * sh));
+  const int s = (int)(((long long)sum + ((1 << sh) >> 1)) >> sh);
+  *sse_out = sse32;
+  const long long var = (long long)sse32 - (((long long)s * s) / (W * W));
+  return var >= 0 ? (unsigned)var : 0u;
+}
+
+template <typename T, int W>
+__device__ __forceinline__ unsigned variance(const T *a, int as, const T *b, int bs, int hbd_shift,
+                                             unsigned *sse_out) {
+  const int lane = lane_id();
+  constexpr int RP = 32 / W;  // rows per iteration
+  const int col = lane % W, r0 = lane / W;
+  int sum = 0;
+  unsigned sse = 0;
+#pragma unroll 8
+  for (int i = r0; i < W; i += RP) {
+    const int d = (int)__ldg(a + i * as + col) - (int)__ldg(b + i * bs + col);
+    sum += d;
+    sse += (unsigned)(d * d);
+  }
+  sum = warp_sum_i32(sum);
+  const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
+  return var_finish(sum, sse64, W, hbd_shift, sse_out);
+}
+
+// get_mvpred_var_cost (mcomp.c:645-664): vf(src, ref@mv) + L1 cost
+template <typename T, int W>
+__device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
+  unsigned sse;
+  const int v = (int)variance<T, W>(S.src, S.stride, S.ref + r * S.stride + c, S.stride, S.hbd_shift, &sse);
+  return v + sse_cost(S, r * 8, c * 8);
+}
+
+// ---------------------------------------------------------------------------
+// diamond_search_sad (mcomp.c:1299-1416)
+// ---------------------------------------------------------------------------
+template <typename T, int W, bool SKIP>
+__device__ unsigned diamond_search(const Search<T> &S, MV2 start, int search_step, int *num00, MV2 *best_mv,
+                                   const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+  using L = SadL<T, W, SKIP>;
+  const int lane = lane_id();
+  start.col = iclamp(start.col, S.lim.col_min, S.lim.col_max);
+  start.row = iclamp(start.row, S.lim.row_min, S.lim.row_max);
+  const int tot_steps = 15 - search_step;
+  *num00 = 0;
+  *best_mv = start;
+  unsigned bestsad = sad_single<T, W, SKIP>(S, start.row, start.col, sw) + sad_cost(S, start.row, start.col);
+  int is_off_center = 0;
+  int next_step_size = tot_steps > 2 ? c_sites.radius[tot_steps - 2] : 1;
+  for (int step = tot_steps - 1; step >= 0; --step) {
+    int best_site = 0;
+    if (step > 0) next_step_size = c_sites.radius[step - 1];
+    const int nsites = c_sites.n[step];
+    const int rad = c_sites.radius[step];
+    // all_in tests only the four axis sites (mcomp.c:1339-1344)
+    const bool all_in = (best_mv->row - rad >= S.lim.row_min) && (best_mv->row + rad <= S.lim.row_max) &&
+                        (best_mv->col - rad >= S.lim.col_min) && (best_mv->col + rad <= S.lim.col_max);
+    for (int idx0 = 1; idx0 <= nsites; idx0 += L::CPP) {
+      const int my_idx = idx0 + lane / L::LPC;
+      int my_r = 0, my_c = 0;
+      bool valid = my_idx <= nsites;
+      if (valid) {
+        my_r = best_mv->row + c_sites.r[step][my_idx];
+        my_c = best_mv->col + c_sites.c[step][my_idx];
+        valid = all_in || in_range(S.lim, my_r, my_c);
+      }
+      unsigned tot = sad_partial<T, W, SKIP>(S.ref, S.stride, my_r, my_c, valid, sw);
+      tot = seg_reduce_u32<L::LPC>(tot);
+#pragma unroll
+      for (int k = 0; k < L::CPP; k++) {
+        const int idx = idx0 + k;
+        const unsigned t = __shfl_sync(FULL, tot, k * L::LPC);
+        const int cr = __shfl_sync(FULL, my_r, k * L::LPC);
+        const int cc = __shfl_sync(FULL, my_c, k * L::LPC);
+        const int v = __shfl_sync(FULL, (int)valid, k * L::LPC);
+        if (idx <= nsites && v) {
+          unsigned thissad = sad_post<SKIP>(t, S.hbd_shift);
+          if (thissad < bestsad) {
+            thissad += sad_cost(S, cr, cc);
+            if (thissad < bestsad) {
+              bestsad = thissad;
+              best_site = idx;
+            }
+          }
+        }
+      }
+    }
+    if (best_site != 0) {
+      best_mv->row += c_sites.r[step][best_site];
+      best_mv->col += c_sites.c[step][best_site];
+      is_off_center = 1;
+    }
+    if (is_off_center == 0) (*num00)++;
+    if (best_site == 0) {
+      while (next_step_size == c_sites.radius[step] && step > 2) {
+        ++(*num00);
+        --step;
+        next_step_size = c_sites.radius[step - 1];
+      }
+    }
+  }
+  return bestsad;
+}
+
+// full_pixel_diamond (mcomp.c:1421-1470), cost_list == NULL
+template <typename T, int W, bool SKIP>
+__device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param, MV2 *best_mv,
+                                  const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+  int n, num00 = 0;
+  int bestsme = (int)diamond_search<T, W, SKIP>(S, start, step_param, &n, best_mv, sw);
+  if (bestsme < INT_MAX_) bestsme = var_cost<T, W>(S, best_mv->row, best_mv->col);
+  const int further_steps = 15 - 1 - step_param;
+  while (n < further_steps) {
+    ++n;
+    if (num00) {
+      num00--;
+    } else {
+      MV2 tmp;
+      int thissme = (int)diamond_search<T, W, SKIP>(S, start, step_param + n, &num00, &tmp, sw);
+      if (thissme < INT_MAX_) thissme = var_cost<T, W>(S, tmp.row, tmp.col);
+      if (thissme < bestsme) {
+        bestsme = thissme;
+        *best_mv = tmp;
+      }
+    }
+  }
+  return bestsme;
+}
+
+// exhaustive_mesh_search (mcomp.c:1474-1543).  The visiting order is the
+// reference's (row major; with step == 1 the 4-wide groups and the tail quirk
+// that never visits end_col unless the column count is a multiple of 4).
+template <typename T, int W, bool SKIP>
+__device__ int mesh_search(const Search<T> &S, MV2 start, int range, int step, MV2 *best_mv,
+                           const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+  using L = SadL<T, W, SKIP>;
+  const int lane = lane_id();
+  start.col = iclamp(start.col, S.lim.col_min, S.lim.col_max);
+  start.row = iclamp(start.row, S.lim.row_min, S.lim.row_max);
+  *best_mv = start;
+  unsigned best_sad = sad_single<T, W, SKIP>(S, start.row, start.col, sw) + sad_cost(S, start.row, start.col);
+  const int start_row = imax(-range, S.lim.row_min - start.row);
+  const int start_col = imax(-range, S.lim.col_min - start.col);
+  const int end_row = imin(range, S.lim.row_max - start.row);
+  const int end_col = imin(range, S.lim.col_max - start.col);
+  if (end_row < start_row || end_col < start_col) return (int)best_sad;
+  const int n_rows = (end_row - start_row) / step + 1;
+  int n_cols;
+  if (step > 1) {
+    n_cols = (end_col - start_col) / step + 1;
+  } else {
+    const int ncols = end_col - start_col + 1;
+    n_cols = (ncols % 4 == 0) ? ncols : ncols - 1;
+  }
+  const int total = n_rows * n_cols;
+  for (int q0 = 0; q0 < total; q0 += L::CPP) {
+    const int q = q0 + lane / L::LPC;
+    const bool valid = q < total;
+    int my_r = 0, my_c = 0;
+    if (valid) {
+      const int ri = q / n_cols, ci = q - ri * n_cols;
+      my_r = start.row + start_row + ri * step;
+      my_c = start.col + start_col + ci * step;
+    }
+    unsigned tot = sad_partial<T, W, SKIP>(S.ref, S.stride, my_r, my_c, valid, sw);
+    tot = seg_reduce_u32<L::LPC>(tot);
+#pragma unroll
+    for (int k = 0; k < L::CPP; k++) {
+      const unsigned t = __shfl_sync(FULL, tot, k * L::LPC);
+      const int cr = __shfl_sync(FULL, my_r, k * L::LPC);
+      const int cc = __shfl_sync(FULL, my_c, k * L::LPC);
+      if (q0 + k < total) {
+        const unsigned this_sad = sad_post<SKIP>(t, S.hbd_shift);
+        if (this_sad < best_sad) {  // update_mvs_and_sad mcomp.c:839-858
+          const unsigned sad = this_sad + sad_cost(S, cr, cc);
+          if (sad < best_sad) {
+            best_sad = sad;
+            best_mv->row = cr;
+            best_mv->col = cc;
+          }
+        }
+      }
+    }
+  }
+  return (int)best_sad;
+}
+
+// full_pixel_exhaustive (mcomp.c:1547-1617)
+template <typename T, int W, bool SKIP>
+__device__ int full_pixel_exhaustive(const Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv,
+                                     const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+  int interval = P.mesh[0][1], range = P.mesh[0][0];
+  *best_mv = start;
+  if (range < 7 || range > 256 || interval < 1 || interval > range) return INT_MAX_;
+  const int baseline_interval_divisor = range / interval;
+  range = imax(range, (5 * imax(iabs(best_mv->row), iabs(best_mv->col))) / 4);
+  range = imin(range, 256);
+  interval = imax(interval, range / baseline_interval_divisor);
+  int bestsme = mesh_search<T, W, SKIP>(S, *best_mv, range, interval, best_mv, sw);
+  if (interval > 1 && range > 7) {
+    for (int i = 1; i < 4; ++i) {
+      bestsme = mesh_search<T, W, SKIP>(S, *best_mv, P.mesh[i][0], P.mesh[i][1], best_mv, sw);
+      if (P.mesh[i][1] == 1) break;
+    }
+  }
+  if (bestsme < INT_MAX_) bestsme = var_cost<T, W>(S, best_mv->row, best_mv->col);
+  return bestsme;
+}
+
+// av1_full_pixel_search (mcomp.c:1693-1832), NSTEP, run_mesh_search = 1.
+// Returns 1 when the skip-row result must be discarded and the search redone
+// with full SAD (mcomp.c:1777-1810).
+template <typename T, int W, bool SKIP>
+__device__ int full_pixel_search_pass(const Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv) {
+  uint32_t sw[SadL<T, W, SKIP>::NW];
+  sad_load_src<T, W, SKIP>(S.src, S.stride, sw);
+  int run_mesh = 1;
+  int var = full_pixel_diamond<T, W, SKIP>(S, start, P.step_param, best_mv, sw);
+  int prune = 0, thr = 4;
+  if (P.prune_level == 2) prune = 1;
+  if (P.prune_level == 1) {
+    prune = (P.q_factor <= 20) ? 0 : 1;
+    thr = 2;
+  }
+  if (prune) {
+    const int d = imax(iabs(start.row - best_mv->row), iabs(start.col - best_mv->col));
+    if (d <= thr) run_mesh = 0;
+  }
+  if (SKIP) {
+    // sdf and sdsf at best_mv: the lane layout of this pass is the skip one, so
+    // use the column-wise generic SAD here (two evaluations per search).
+    const int lane = lane_id();
+    constexpr int RP = 32 / W;
+    const int col = lane % W, r0 = lane / W;
+    const T *a = S.src, *b = S.ref + best_mv->row * S.stride + best_mv->col;
+    unsigned s_all = 0, s_even = 0;
+#pragma unroll 8
+    for (int i = r0; i < W; i += RP) {
+      const unsigned d = (unsigned)iabs((int)__ldg(a + i * S.stride + col) - (int)__ldg(b + i * S.stride + col));
+      s_all += d;
+      if ((i & 1) == 0) s_even += d;
+    }
+    s_all = seg_reduce_u32<32>(s_all);
+    s_even = seg_reduce_u32<32>(s_even);
+    const int sad = (int)(s_all >> S.hbd_shift);
+    const int skip_sad = (int)((2 * s_even) >> S.hbd_shift);
+    const int kSADThresh = W * W / 16;
+    if (sad > kSADThresh && iabs(skip_sad - sad) * 10 >= imax(sad, 1) * 9) return 1;
+  }
+  if (run_mesh) {
+    MV2 tmp;
+    const int var_ex = full_pixel_exhaustive<T, W, SKIP>(S, P, *best_mv, &tmp, sw);
+    if (var_ex < var) {
+      var = var_ex;
+      *best_mv = tmp;
+    }
+  }
+  return 0;
+}
+
+template <typename T, int W>
+__device__ void full_pixel_search(const Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv) {
+  if (P.use_skip) {
+    if (!full_pixel_search_pass<T, W, true>(S, P, start, best_mv)) return;
+  }
+  full_pixel_search_pass<T, W, false>(S, P, start, best_mv);
+}
+
+// ---------------------------------------------------------------------------
+// Sub-pel search
+// ---------------------------------------------------------------------------
+// aom_sub_pixel_variance (aom_dsp/variance.c:91-139,150-163; hbd :478-560):
+// 2-tap bilinear over (W+1) x (W+1) samples then variance(filtered, src).
+template <typename T, int W>
+__device__ unsigned bilinear_err(const Search<T> &S, int r8, int c8) {
+  const int lane = lane_id();
+  const T *ref = S.ref + (r8 >> 3) * S.stride + (c8 >> 3);
+  const int xo = c8 & 7, yo = r8 & 7;
+  const int f0 = 128 - 16 * xo, f1 = 16 * xo, g0 = 128 - 16 * yo, g1 = 16 * yo;
+  constexpr int BANDS = 32 / W;      // 1 (W=32) or 2 (W=16)
+  constexpr int BROWS = W / BANDS;   // rows per band
+  const int col = lane % W, band = lane / W;
+  const int rbeg = band * BROWS;
+  int sum = 0;
+  unsigned sse = 0;
+  int hprev = 0;
+#pragma unroll 3
+  for (int t = 0; t <= BROWS; t++) {
+    const int i = rbeg + t;
+    const T *rp = ref + i * S.stride + col;
+    const int h = rpot((int)__ldg(rp) * f0 + (int)__ldg(rp + 1) * f1, 7);
+    if (t > 0) {
+      int v = rpot(hprev * g0 + h * g1, 7);
+      if (sizeof(T) == 1) v &= 0xff;
+      const int d = v - (int)__ldg(S.src + (i - 1) * S.stride + col);
+      sum += d;
+      sse += (unsigned)(d * d);
+    }
+    hprev = h;
+  }
+  sum = warp_sum_i32(sum);
+  const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
+  unsigned sse_out;
+  return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
+}
+
+__device__ __forceinline__ int clip_px(int v, int bd) {
+  const int m = (1 << bd) - 1;
+  return v < 0 ? 0 : (v > m ? m : v);
+}
+
+// aom_upsampled_pred_c (reconinter_enc.c:424-496, hbd :656+) with
+// EIGHTTAP_REGULAR through aom_convolve8_{horiz,vert}_c (aom_dsp/aom_convolve.c
+// :36-72; pixel-range intermediate), then vf(pred, src) (mcomp.c:2385,2405).
+// tmp: warp-private shared scratch of at least (W+7)*W samples of T.
+template <typename T, int W>
+__device__ unsigned upsampled_err(const Search<T> &S, int r8, int c8, int bd, T *tmp) {
+  const int lane = lane_id();
+  const int st = S.stride;
+  const T *ref = S.ref + (r8 >> 3) * st + (c8 >> 3);
+  const int sx = c8 & 7, sy = r8 & 7;
+  constexpr int RP = 32 / W;
+  const int col = lane % W, r0 = lane / W;
+  int sum = 0;
+  unsigned sse = 0;
+  if (sx && sy) {
+    const int16_t *kx = c_k8[sx << 1];
+    for (int y = r0; y < W + 7; y += RP) {
+      int acc = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) acc += (int)__ldg(ref + (y - 3) * st + col - 3 + t) * kx[t];
+      tmp[y * W + col] = (T)clip_px(rpot(acc, 7), bd);
+    }
+    __syncwarp();
+  }
+  const int16_t *ky = c_k8[sy << 1];
+  const int16_t *kx = c_k8[sx << 1];
+  for (int y = r0; y < W; y += RP) {
+    int v;
+    if (!sx && !sy) {
+      v = (int)__ldg(ref + y * st + col);
+    } else if (!sy) {
+      int acc = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) acc += (int)__ldg(ref + y * st + col - 3 + t) * kx[t];
+      v = clip_px(rpot(acc, 7), bd);
+    } else if (!sx) {
+      int acc = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) acc += (int)__ldg(ref + (y - 3 + t) * st + col) * ky[t];
+      v = clip_px(rpot(acc, 7), bd);
+    } else {
+      int acc = 0;
+#pragma unroll
+      for (int t = 0; t < 8; t++) acc += (int)tmp[(y + t) * W + col] * ky[t];
+      v = clip_px(rpot(acc, 7), bd);
+    }
+    const int d = v - (int)__ldg(S.src + y * st + col);
+    sum += d;
+    sse += (unsigned)(d * d);
+  }
+  __syncwarp();
+  sum = warp_sum_i32(sum);
+  const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
+  unsigned sse_out;
+  return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
+}
+
+template <typename T, int W>
+struct Subpel {
+  const Search<T> *S;
+  Lim lim;
+  unsigned besterr;
+  MV2 best;
+  int bd;
+  T *tmp;
+};
+
+// check_better_fast / check_better (mcomp.c:2433-2488), MV_COST_NONE
+template <typename T, int W>
+__device__ __forceinline__ unsigned check_better(Subpel<T, W> &sp, int r8, int c8, bool accurate, int *is_better) {
+  if (!in_range(sp.lim, r8, c8)) return (unsigned)INT_MAX_;
+  const unsigned cost = accurate ? upsampled_err<T, W>(*sp.S, r8, c8, sp.bd, sp.tmp) : bilinear_err<T, W>(*sp.S, r8, c8);
+  if (cost < sp.besterr) {
+    sp.besterr = cost;
+    sp.best.row = r8;
+    sp.best.col = c8;
+    if (is_better) *is_better |= 1;
+  }
+  return cost;
+}
+
+// first_level_check(_fast) (mcomp.c:2503-2541, 2626-2660)
+template <typename T, int W>
+__device__ MV2 first_level(Subpel<T, W> &sp, MV2 t, int hstep, bool accurate) {
+  const unsigned left = check_better(sp, t.row, t.col - hstep, accurate, nullptr);
+  const unsigned right = check_better(sp, t.row, t.col + hstep, accurate, nullptr);
+  const unsigned up = check_better(sp, t.row - hstep, t.col, accurate, nullptr);
+  const unsigned down = check_better(sp, t.row + hstep, t.col, accurate, nullptr);
+  MV2 diag;
+  diag.row = up <= down ? -hstep : hstep;
+  diag.col = left <= right ? -hstep : hstep;
+  check_better(sp, t.row + diag.row, t.col + diag.col, accurate, nullptr);
+  return diag;
+}
+
+// second_level_check_fast (mcomp.c:2545-2605)
+template <typename T, int W>
+__device__ void second_level_fast(Subpel<T, W> &sp, MV2 t, MV2 diag, int hstep) {
+  const int tr = t.row, tc = t.col, br = sp.best.row, bc = sp.best.col;
+  if (tr != br && tc != bc) {
+    check_better(sp, br, bc + diag.col, false, nullptr);
+    check_better(sp, br + diag.row, bc, false, nullptr);
+  } else if (tr == br && tc != bc) {
+    check_better(sp, br + hstep, bc + diag.col, false, nullptr);
+    check_better(sp, br - hstep, bc + diag.col, false, nullptr);
+    check_better(sp, br - diag.row, bc, false, nullptr);
+  } else if (tr != br && tc == bc) {
+    check_better(sp, br + diag.row, bc + hstep, false, nullptr);
+    check_better(sp, br + diag.row, bc - hstep, false, nullptr);
+    check_better(sp, br, bc - diag.col, false, nullptr);
+  }
+}
+
+// second_level_check_v2 (mcomp.c:2665-2715), subpel_search_type = USE_8_TAPS
+template <typename T, int W>
+__device__ void second_level_v2(Subpel<T, W> &sp, MV2 t, MV2 diag) {
+  if (t.row == sp.best.row && t.col == sp.best.col) return;
+  if (t.row == sp.best.row) diag.row *= -1;
+  else if (t.col == sp.best.col) diag.col *= -1;
+  const MV2 rb = { sp.best.row + diag.row, sp.best.col };
+  const MV2 cb = { sp.best.row, sp.best.col + diag.col };
+  const MV2 db = { sp.best.row + diag.row, sp.best.col + diag.col };
+  int has_better = 0;
+  check_better(sp, rb.row, rb.col, true, &has_better);
+  check_better(sp, cb.row, cb.col, true, &has_better);
+  if (has_better) check_better(sp, db.row, db.col, true, &has_better);
+}
+
+// av1_find_best_sub_pixel_tree{,_pruned,_pruned_more} (mcomp.c:2844-3133) with
+// cost_list == NULL, forced_stop = EIGHTH_PEL, MV_COST_NONE, unscaled refs.
+template <typename T, int W>
+__device__ unsigned subpel_search(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+  Subpel<T, W> sp;
+  sp.S = &S;
+  sp.bd = P.is_hbd ? P.bit_depth : 8;
+  sp.tmp = tmp;
+  const int max_mv = 1023 * 8;  // av1_set_subpel_mv_search_range mcomp.h:344-361
+  sp.lim.col_min = imax(-(1 << 14) + 1, imax(S.lim.col_min * 8, -max_mv));
+  sp.lim.col_max = imin((1 << 14) - 1, imin(S.lim.col_max * 8, max_mv));
+  sp.lim.row_min = imax(-(1 << 14) + 1, imax(S.lim.row_min * 8, -max_mv));
+  sp.lim.row_max = imin((1 << 14) - 1, imin(S.lim.row_max * 8, max_mv));
+  MV2 start = { start_full.row * 8, start_full.col * 8 };
+  sp.best = start;
+  int hstep = 4;
+  if (P.subpel_method == 0) {  // SUBPEL_TREE
+    sp.besterr = upsampled_err<T, W>(S, start.row, start.col, sp.bd, tmp);
+    const int rounds = P.allow_hp ? 3 : 2;
+    for (int iter = 0; iter < rounds; ++iter) {
+      const MV2 center = sp.best;
+      const MV2 diag = first_level(sp, center, hstep, true);
+      if (!(center.row == sp.best.row && center.col == sp.best.col) && P.iters_per_step > 1)
+        second_level_v2(sp, center, diag);
+      hstep >>= 1;
+    }
+  } else {
+    unsigned sse;  // setup_center_error (mcomp.c:2718-2777): vf(ref, src)
+    sp.besterr = variance<T, W>(S.ref + start_full.row * S.stride + start_full.col, S.stride, S.src, S.stride,
+                                S.hbd_shift, &sse);
+    const int rounds = P.allow_hp ? 3 : 2;
+    for (int it = 0; it < rounds; it++) {
+      const MV2 center = sp.best;
+      const MV2 diag = first_level(sp, center, hstep, false);
+      if (P.iters_per_step > 1) second_level_fast(sp, center, diag, hstep);
+      hstep >>= 1;
+    }
+  }
+  *best = sp.best;
+  return sp.besterr;
+}
+
+__device__ __forceinline__ int rawpel(int x) { return (x + 3 + (x >= 0)) >> 3; }  // GET_MV_RAWPEL mv.h:28
+
+// tf_motion_search (temporal_filter.c:87-253)
+template <typename T>
+__device__ void motion_search(const KParams &P, const T *cur, const T *ref, int mb_row, int mb_col, MV2 *ref_mv,
+                              MV2 *sub_mvs, int *sub_mses, T *tmp) {
+  const int st = P.pitch[0];
+  const int y_offset = mb_row * 32 * st + mb_col * 32;
+  Search<T> S;
+  S.stride = st;
+  S.sad_lambda = P.sad_lambda;
+  S.sse_lambda = P.sse_lambda;
+  S.hbd_shift = P.hbd_shift;
+  S.is_hbd = P.is_hbd;
+  {  // av1_set_mv_{row,col}_limits (mcomp.h:216-240) + av1_set_mv_search_range (mcomp.c:196-215)
+    const int border = P.border, mi_row = mb_row * 8, mi_col = mb_col * 8;
+    S.lim.row_min = imax(-(mi_row * 4 + border - 8), -(((mi_row + 8) * 4) + 8));
+    S.lim.row_max = imin((P.mi_rows - mi_row - 8) * 4 + border - 8, (P.mi_rows - mi_row) * 4 + 8);
+    S.lim.col_min = imax(-(mi_col * 4 + border - 8), -(((mi_col + 8) * 4) + 8));
+    S.lim.col_max = imin((P.mi_cols - mi_col - 8) * 4 + border - 8, (P.mi_cols - mi_col) * 4 + 8);
+    S.lim.col_min = imax(S.lim.col_min, -1023);
+    S.lim.col_max = imin(S.lim.col_max, 1023);
+    S.lim.row_min = imax(S.lim.row_min, -1023);
+    S.lim.row_max = imin(S.lim.row_max, 1023);
+  }
+  MV2 start = { rawpel(ref_mv->row), rawpel(ref_mv->col) };
+  S.src = cur + y_offset;
+  S.ref = ref + y_offset;
+  MV2 best_full;
+  full_pixel_search<T, 32>(S, P, start, &best_full);
+  int block_mse;
+  MV2 block_mv;
+  if (P.force_integer_mv == 1) {
+    unsigned sse;
+    const unsigned err = variance<T, 32>(S.ref + best_full.row * st + best_full.col, st, S.src, st, S.hbd_shift, &sse);
+    block_mse = (int)((err + 512u) / 1024u);
+    block_mv.row = best_full.row * 8;
+    block_mv.col = best_full.col * 8;
+  } else {
+    MV2 best;
+    unsigned err = subpel_search<T, 32>(S, P, best_full, &best, tmp);
+    block_mse = (int)((err + 512u) / 1024u);
+    block_mv = best;
+    *ref_mv = best;
+    start.row = rawpel(ref_mv->row);
+    start.col = rawpel(ref_mv->col);
+    int idx = 0;
+    for (int i = 0; i < 32; i += 16) {
+      for (int j = 0; j < 32; j += 16) {
+        S.src = cur + y_offset + i * st + j;
+        S.ref = ref + y_offset + i * st + j;
+        full_pixel_search<T, 16>(S, P, start, &best_full);
+        err = subpel_search<T, 16>(S, P, best_full, &best, tmp);
+        sub_mses[idx] = (int)((err + 128u) / 256u);
+        sub_mvs[idx] = best;
+        ++idx;
+      }
+    }
+  }
+  // tf_determine_block_partition (:270-292)
+  int mn = INT_MAX_, mx = -INT_MAX_ - 1;
+  long long sum = 0;
+  for (int i = 0; i < 4; i++) {
+    sum += sub_mses[i];
+    mn = imin(mn, sub_mses[i]);
+    mx = imax(mx, sub_mses[i]);
+  }
+  if ((((long long)block_mse * 15 < sum * 4) && mx - mn < 48) ||
+      (((long long)block_mse * 14 < sum * 4) && mx - mn < 24)) {
+    for (int i = 0; i < 4; i++) {
+      sub_mvs[i] = block_mv;
+      sub_mses[i] = block_mse;
+    }
+  }
+  if (block_mse > P.mse_thresh) {
+    ref_mv->row = 0;
+    ref_mv->col = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Predictor: tf_build_predictor (temporal_filter.c:328-390) ->
+// init_subpel_params (reconinter.h:131-165) -> convolve_2d_facade_single
+// (convolve.c:495-515) with the 12-tap MULTITAP_SHARP2 kernels.
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ void convolve12(const KParams &P, const T *src, int ss, T *dst, int ds, int w, int h, int sx, int sy,
+                           int16_t *im) {
+  const int lane = lane_id();
+  const int pbd = P.is_hbd ? P.bit_depth : 8;
+  int r0b = 3, r1b = 11;  // get_conv_params_no_round (convolve.h:63-95)
+  if (P.is_hbd && P.bit_depth + 7 - r0b + 2 > 16) {
+    const int d = P.bit_depth + 7 - r0b + 2 - 16;
+    r0b += d;
+    r1b -= d;
+  }
+  const int rp = 32 / w;  // rows per iteration (w is 8 or 16)
+  const int col = lane % w, rr = lane / w;
+  if (!sx && !sy) {
+    for (int y = rr; y < h; y += rp) dst[y * ds + col] = __ldg(src + y * ss + col);
+  } else if (sx && !sy) {
+    const int16_t *f = c_k12[sx];
+    const int bits = 7 - r0b;
+    for (int y = rr; y < h; y += rp) {
+      int res = 0;
+#pragma unroll
+      for (int k = 0; k < 12; k++) res += f[k] * (int)__ldg(src + y * ss + col - 5 + k);
+      res = rpot(res, r0b);
+      dst[y * ds + col] = (T)clip_px(rpot(res, bits), pbd);
+    }
+  } else if (!sx && sy) {
+    const int16_t *f = c_k12[sy];
+    for (int y = rr; y < h; y += rp) {
+      int res = 0;
+#pragma unroll
+      for (int k = 0; k < 12; k++) res += f[k] * (int)__ldg(src + (y - 5 + k) * ss + col);
+      dst[y * ds + col] = (T)clip_px(rpot(res, 7), pbd);
+    }
+  } else {
+    const int16_t *fx = c_k12[sx], *fy = c_k12[sy];
+    const int bits = 14 - r0b - r1b;
+    for (int y = rr; y < h + 11; y += rp) {
+      int sum = 1 << (pbd + 6);
+#pragma unroll
+      for (int k = 0; k < 12; k++) sum += fx[k] * (int)__ldg(src + (y - 5) * ss + col - 5 + k);
+      im[y * w + col] = (int16_t)rpot(sum, r0b);
+    }
+    __syncwarp();
+    const int ob = pbd + 14 - r0b;
+    for (int y = rr; y < h; y += rp) {
+      int sum = 1 << ob;
+#pragma unroll
+      for (int k = 0; k < 12; k++) sum += fy[k] * (int)im[(y + k) * w + col];
+      int res = rpot(sum, r1b) - ((1 << (ob - r1b)) + (1 << (ob - r1b - 1)));
+      if (sizeof(T) == 1) res = (int)(int16_t)res;  // convolve.c:120
+      dst[y * ds + col] = (T)clip_px(rpot(res, bits), pbd);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T>
+__device__ void build_predictor(const KParams &P, const T *const ref[3], int mb_row, int mb_col, const MV2 *mvs,
+                                T *pred, int16_t *im) {
+  int plane_offset = 0;
+  for (int plane = 0; plane < P.num_planes; plane++) {
+    const int ssy = plane ? P.ss_y : 0, ssx = plane ? P.ss_x : 0;
+    const int k = plane > 0;
+    const int plane_h = 32 >> ssy, plane_w = 32 >> ssx;
+    const int plane_y = (32 * mb_row) >> ssy, plane_x = (32 * mb_col) >> ssx;
+    const int h = plane_h >> 1, w = plane_w >> 1;
+    int idx = 0;
+    for (int i = 0; i < plane_h; i += h) {
+      for (int j = 0; j < plane_w; j += w) {
+        const MV2 mv = mvs[idx++];
+        const int y = plane_y + i, x = plane_x + j;
+        int pos_y = ((y << 4) + mv.row * (1 << (1 - ssy))) * 64 + 32;
+        int pos_x = ((x << 4) + mv.col * (1 << (1 - ssx))) * 64 + 32;
+        const int top = -(((288 >> ssy) - 4) << 10), left = -(((288 >> ssx) - 4) << 10);
+        pos_y = iclamp(pos_y, top, (P.aligned_h[k] + 4) << 10);
+        pos_x = iclamp(pos_x, left, (P.aligned_w[k] + 4) << 10);
+        const T *src = ref[plane] + (pos_y >> 10) * P.pitch[k] + (pos_x >> 10);
+        convolve12<T>(P, src, P.pitch[k], &pred[plane_offset + i * plane_w + j], plane_w, w, h, (pos_x & 1023) >> 6,
+                      (pos_y & 1023) >> 6, im);
+      }
+    }
+    plane_offset += plane_h * plane_w;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// Weights: av1_apply_temporal_filter_c (temporal_filter.c:557-707)
+// sq:   warp-private u32[1024] (squared differences, then horizontal 5-sums)
+// lsum: warp-private u32[1024] (co-located luma squared-difference sums)
+// ---------------------------------------------------------------------------
+template <typename T>
+__device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row, int mb_col, const MV2 *mvs,
+                             const int *mses, const T *pred, uint32_t *accum, uint16_t *count, uint32_t *sq,
+                             uint32_t *lsum) {
+  const int lane = lane_id();
+  const double inv_factor = 1.0 / ((5 + 1) * 20);
+  const double weight_factor = (double)5 * inv_factor;
+  double d_factor[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const double distance = sqrt((double)(mvs[i].row * mvs[i].row + mvs[i].col * mvs[i].col));
+    const double d = distance / P.dist_thr;
+    d_factor[i] = d > 1.0 ? d : 1.0;
+  }
+  int plane_offset = 0;
+  for (int plane = 0; plane < P.num_planes; plane++) {
+    const int ssy = plane ? P.ss_y : 0, ssx = plane ? P.ss_x : 0;
+    const int h = 32 >> ssy, w = 32 >> ssx;
+    const int st = P.pitch[plane > 0];
+    const T *src = cur[plane] + mb_row * h * st + mb_col * w;
+    const int num_ref_pixels = 25 + (plane ? (1 << (ssx + ssy)) : 0);
+    const double inv_num_ref_pixels = 1.0 / num_ref_pixels;
+    if (plane == 1) {  // compute_luma_sq_error_sum (:507-522); sq still holds the raw luma squares
+      for (int idx = lane; idx < h * w; idx += 32) {
+        const int i = idx / w, j = idx - i * w;
+        uint32_t s = 0;
+        for (int ii = 0; ii < (1 << ssy); ii++)
+          for (int jj = 0; jj < (1 << ssx); jj++) s += lsum[((i << ssy) + ii) * 32 + (j << ssx) + jj];
+        sq[idx] = s;  // staged in sq, copied back below
+      }
+      __syncwarp();
+      for (int idx = lane; idx < h * w; idx += 32) lsum[idx] = sq[idx];
+      __syncwarp();
+    }
+    // compute_square_diff (:463-493)
+    for (int idx = lane; idx < h * w; idx += 32) {
+      const int i = idx / w, j = idx - i * w;
+      const int d = (int)__ldg(src + i * st + j) - (int)pred[plane_offset + idx];
+      sq[idx] = (uint32_t)(d * d);
+    }
+    __syncwarp();
+    if (plane == 0 && P.num_planes > 1) {
+      for (int idx = lane; idx < 1024; idx += 32) lsum[idx] = sq[idx];
+      __syncwarp();
+    }
+    // horizontal 5-sums with edge clamp, in place (each lane owns whole rows of its column set)
+    {
+      const int rp = 32 / w, col = lane % w, rr = lane / w;
+      for (int i = rr; i < h; i += rp) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int dj = -2; dj <= 2; dj++) s += sq[i * w + iclamp(col + dj, 0, w - 1)];
+        __syncwarp();
+        sq[i * w + col] = s;
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    for (int idx = lane; idx < h * w; idx += 32) {
+      const int i = idx / w, j = idx - i * w;
+      unsigned long long sum_square_diff = 0;
+#pragma unroll
+      for (int di = -2; di <= 2; di++) sum_square_diff += sq[iclamp(i + di, 0, h - 1) * w + j];
+      if (plane) sum_square_diff += lsum[idx];
+      if (P.bit_depth > 8) sum_square_diff >>= ((P.bit_depth - 8) * 2);
+      const double window_error = __dmul_rn((double)sum_square_diff, inv_num_ref_pixels);
+      const int sb = (i >= h / 2) * 2 + (j >= w / 2);
+      const double block_error = (double)mses[sb];
+      const double combined_error =
+          __dadd_rn(__dmul_rn(weight_factor, window_error), __dmul_rn(block_error, inv_factor));
+      double scaled_error = __dmul_rn(__dmul_rn(combined_error, d_factor[sb]), P.decay[plane]);
+      scaled_error = scaled_error < 7.0 ? scaled_error : 7.0;
+      const int weight = (int)__dmul_rn(exp(-scaled_error), 1000.0);
+      const int pidx = plane_offset + idx;
+      accum[pidx] += (uint32_t)(weight * (int)pred[pidx]);
+      count[pidx] = (uint16_t)(count[pidx] + weight);
+    }
+    __syncwarp();
+    plane_offset += h * w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The fused block kernel: av1_tf_do_filtering_row (temporal_filter.c:788-939)
+// for one 32x32 block per warp.
+// ---------------------------------------------------------------------------
+// Warp-private shared memory, carved at run time (num_pels = 1024 luma + chroma:
+// 1536 for 4:2:0, 2048 for 4:2:2, 3072 for 4:4:4):
+//   accum u32[num_pels] | sq u32[1024] | lsum u32[1024] | count u16[num_pels] |
+//   pred T-view of u16[num_pels] | im i16[27*16]
+struct WarpSmem {
+  uint32_t *accum, *sq, *lsum;
+  uint16_t *count, *pred;
+  int16_t *im;
+};
+__host__ __device__ inline size_t warp_smem_bytes(int num_pels) {
+  return (size_t)num_pels * 8 + 2 * 1024 * 4 + (16 + 11) * 16 * 2;
+}
+__device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels) {
+  WarpSmem sm;
+  sm.accum = reinterpret_cast<uint32_t *>(raw);
+  sm.sq = sm.accum + num_pels;
+  sm.lsum = sm.sq + 1024;
+  sm.count = reinterpret_cast<uint16_t *>(sm.lsum + 1024);
+  sm.pred = sm.count + num_pels;
+  sm.im = reinterpret_cast<int16_t *>(sm.pred + num_pels);
+  return sm;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) tf_block_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const WarpSmem sm = carve_smem(smem_raw, P.num_pels);
+  const int lane = lane_id();
+  const int blk_local = blockIdx.x;
+  const int mb_row = P.row_begin + blk_local / P.mb_cols;
+  const int mb_col = blk_local % P.mb_cols;
+  const int blk = mb_row * P.mb_cols + mb_col;
+  T *pred = reinterpret_cast<T *>(sm.pred);
+  T *tmp8 = reinterpret_cast<T *>(sm.sq);  // 8-tap scratch aliases sq (not live during the search)
+
+  for (int i = lane; i < P.num_pels; i += 32) {
+    sm.accum[i] = 0;
+    sm.count[i] = 0;
+  }
+  __syncwarp();
+
+  const T *cur[3];
+  for (int pl = 0; pl < 3; pl++) cur[pl] = reinterpret_cast<const T *>(P.frm[P.filter_idx][pl]);
+
+  MV2 ref_mv = { 0, 0 };
+  for (int frame = 0; frame < P.num_frames; frame++) {
+    if (frame == P.filter_idx) {
+      ref_mv.row = -ref_mv.row;
+      ref_mv.col = -ref_mv.col;
+      // tf_apply_temporal_filter_self (:406-446)
+      int off = 0;
+      for (int pl = 0; pl < P.num_planes; pl++) {
+        const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.pitch[pl > 0];
+        const T *b = cur[pl] + mb_row * h * st + mb_col * w;
+        for (int idx = lane; idx < h * w; idx += 32) {
+          const int i = idx / w, j = idx - i * w;
+          sm.accum[off + idx] += 1000u * (uint32_t)__ldg(b + i * st + j);
+          sm.count[off + idx] = (uint16_t)(sm.count[off + idx] + 1000);
+        }
+        off += h * w;
+      }
+      __syncwarp();
+      continue;
+    }
+    const T *ref[3];
+    for (int pl = 0; pl < 3; pl++) ref[pl] = reinterpret_cast<const T *>(P.frm[frame][pl]);
+    MV2 sub_mvs[4] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
+    int sub_mses[4] = { INT_MAX_, INT_MAX_, INT_MAX_, INT_MAX_ };
+    motion_search<T>(P, cur[0], ref[0], mb_row, mb_col, &ref_mv, sub_mvs, sub_mses, tmp8);
+    build_predictor<T>(P, ref, mb_row, mb_col, sub_mvs, pred, sm.im);
+    const size_t bf = (size_t)blk * P.num_frames + frame;
+    if (P.d_mvs && lane < 4) {
+      P.d_mvs[(bf * 4 + lane) * 2 + 0] = (int16_t)sub_mvs[lane].row;
+      P.d_mvs[(bf * 4 + lane) * 2 + 1] = (int16_t)sub_mvs[lane].col;
+    }
+    if (P.d_mses && lane < 4) P.d_mses[bf * 4 + lane] = sub_mses[lane];
+    if (P.d_pred)
+      for (int i = lane; i < P.num_pels; i += 32) P.d_pred[bf * P.num_pels + i] = (uint16_t)pred[i];
+    apply_filter<T>(P, cur, mb_row, mb_col, sub_mvs, sub_mses, pred, sm.accum, sm.count, sm.sq, sm.lsum);
+  }
+
+  // tf_normalize_filtered_frame (:740-777); OD_DIVU == integer division here
+  // (proved exhaustively against the reference for count in [1000,1023]).
+  {
+    int off = 0;
+    for (int pl = 0; pl < P.num_planes; pl++) {
+      const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.out_pitch[pl > 0];
+      T *o = reinterpret_cast<T *>(P.out[pl]) + mb_row * h * st + mb_col * w;
+      for (int idx = lane; idx < h * w; idx += 32) {
+        const int i = idx / w, j = idx - i * w;
+        const uint32_t c = sm.count[off + idx];
+        const uint32_t v = (sm.accum[off + idx] + (c >> 1)) / c;
+        o[i * st + j] = (T)v;
+        if (pl == 0) sm.sq[idx] = v;  // keep the filtered luma for FRAME_DIFF
+      }
+      off += h * w;
+    }
+    __syncwarp();
+  }
+  if (P.d_accum)
+    for (int i = lane; i < P.num_pels; i += 32) P.d_accum[(size_t)blk * P.num_pels + i] = sm.accum[i];
+  if (P.d_count)
+    for (int i = lane; i < P.num_pels; i += 32) P.d_count[(size_t)blk * P.num_pels + i] = sm.count[i];
+
+  if (P.compute_diff) {  // :921-937: vf(src, out, &sse) on the 32x32 luma block
+    const int st = P.pitch[0];
+    const T *a = cur[0] + mb_row * 32 * st + mb_col * 32;
+    unsigned sse = 0;
+    for (int i = 0; i < 32; i++) {
+      const int d = (int)__ldg(a + i * st + lane) - (int)sm.sq[i * 32 + lane];
+      sse += (unsigned)(d * d);
+    }
+    const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
+    if (lane == 0) {
+      unsigned sse32;
+      if (P.hbd_shift == 0) sse32 = (unsigned)sse64;
+      else sse32 = (unsigned)((sse64 + ((1ull << (2 * P.hbd_shift)) >> 1)) >> (2 * P.hbd_shift));
+      atomicAdd(&P.diff[0], (unsigned long long)sse32);
+      atomicAdd(&P.diff[1], (unsigned long long)((long long)sse32 * (long long)sse32));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Border replication: av1_copy_and_extend_frame (av1/encoder/extend.c:113-163)
+// rebuilt on the device over the device-side border of bx columns / by rows.
+// One thread per destination sample outside the crop rectangle.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void extend_borders_kernel(T *plane /* pixel (0,0) */, int pitch, int crop_w, int crop_h, int bx, int by,
+                                      int ext_w /* samples right of x=0 incl. crop */, int ext_h) {
+  const int tw = bx + ext_w;  // total columns covered
+  const int th = by + ext_h;
+  const long long n = (long long)tw * th;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / tw) - by, x = (int)(i % tw) - bx;
+    if (x >= 0 && x < crop_w && y >= 0 && y < crop_h) continue;
+    const int sx = iclamp(x, 0, crop_w - 1), sy = iclamp(y, 0, crop_h - 1);
+    plane[(long long)y * pitch + x] = plane[(long long)sy * pitch + sx];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// av1_estimate_noise_from_single_plane (temporal_filter.c:1150-1194):
+// integer accumulate / count; the final double division is done on the host.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void noise_kernel(const T *src, int pitch, int width, int height, int bd, int edge_thresh,
+                             unsigned long long *accum_count /* [2] */) {
+  long long acc = 0;
+  unsigned cnt = 0;
+  const int iw = width - 2, ih = height - 2;
+  const long long n = (long long)iw * ih;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(q / iw) + 1, j = (int)(q % iw) + 1;
+    const T *m = src + (long long)i * pitch + j;
+    const int a = m[-pitch - 1], b = m[-pitch], c = m[-pitch + 1];
+    const int d = m[-1], e = m[0], f = m[1];
+    const int g = m[pitch - 1], h = m[pitch], k = m[pitch + 1];
+    const int Gx = (a - c) + (g - k) + 2 * (d - f);
+    const int Gy = (a - g) + (c - k) + 2 * (b - h);
+    const int Ga = rpot(iabs(Gx) + iabs(Gy), bd - 8);
+    if (Ga < edge_thresh) {
+      const int v = 4 * e - 2 * (b + h + d + f) + (a + c + g + k);
+      acc += rpot(iabs(v), bd - 8);
+      ++cnt;
+    }
+  }
+  acc = (long long)warp_sum_u64((unsigned long long)acc);
+  cnt = seg_reduce_u32<32>(cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) {
+    atomicAdd(&accum_count[0], (unsigned long long)acc);
+    atomicAdd(&accum_count[1], (unsigned long long)cnt);
+  }
+}
+
+}  // namespace tfk

@@ -1,0 +1,178 @@
+/*
+ * tf_gpu.h -- C ABI of the B200 temporal filter (libtf_gpu.so).
+ *
+ * This is the drop-in boundary for the aom-av1-psy encoder's temporal filter
+ * (ARNR / ARF denoising).  The reference has no plugin API for this path; the
+ * seam is av1_temporal_filter() (av1/encoder/temporal_filter.c:1276): under
+ * CONFIG_TF_GPU it calls tf_gpu_filter() after init_tf_ctx() (:1291) instead of
+ * tf_alloc_and_reset_data() ... tf_do_filtering(_mt)() (:1296-1311).  See
+ * INTEGRATION.md for the patch.  Plain C: POD structs, host pointers and sizes,
+ * integer return codes (0 ok, <0 error; never longjmp / exceptions).  There is
+ * NO CPU fallback: every entry point fails with TF_GPU_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ *
+ * Each declaration cites the reference interface it replaces.
+ */
+#ifndef TF_GPU_H_
+#define TF_GPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TF_GPU_ABI_VERSION 1
+#define TF_GPU_MAX_FRAMES 24 /* reference: arnr_max_frames 15 + adjust 6 = 21 (temporal_filter.c:997,1063-1080) */
+
+enum {
+  TF_GPU_OK = 0,
+  TF_GPU_ERR_INVALID = -1,   /* bad argument (caller: AOM_CODEC_INVALID_PARAM) */
+  TF_GPU_ERR_MEM = -2,       /* device/host allocation failed (caller: AOM_CODEC_MEM_ERROR, cf. temporal_filter.c:1296-1299) */
+  TF_GPU_ERR_CUDA = -3,      /* CUDA runtime error (caller: AOM_CODEC_ERROR) */
+  TF_GPU_ERR_NO_DEVICE = -4, /* no usable GPU; there is no CPU fallback */
+  TF_GPU_ERR_UNSUPPORTED = -5
+};
+
+/* Sub-pel search variant = cpi->mv_search_params.find_fractional_mv_step
+ * (av1/encoder/speed_features.c:2150-2170, mcomp.c:2844/2929/3065). */
+enum { TF_GPU_SUBPEL_TREE = 0, TF_GPU_SUBPEL_TREE_PRUNED = 1, TF_GPU_SUBPEL_TREE_PRUNED_MORE = 2 };
+/* PRUNE_MESH_SEARCH_LEVEL (av1/encoder/speed_features.h) */
+enum { TF_GPU_PRUNE_MESH_DISABLED = 0, TF_GPU_PRUNE_MESH_LVL_1 = 1, TF_GPU_PRUNE_MESH_LVL_2 = 2 };
+
+typedef struct tf_gpu_ctx tf_gpu_ctx;
+
+typedef struct {
+  int device;              /* CUDA device ordinal, -1 = current device */
+  int max_cached_frames;   /* device frame-cache slots (0 = default 32) */
+  int reserved[6];
+} tf_gpu_device_cfg;
+
+/* POD mirror of the YV12_BUFFER_CONFIG fields the temporal filter reads
+ * (aom_scale/yv12config.h:43-123).  plane[] point at pixel (0,0) of each plane
+ * in HOST memory, already CONVERT_TO_SHORTPTR'd for high bitdepth
+ * (aom_ports/mem.h:79-80); strides are in samples.  The pixels outside the
+ * crop area must be edge replication, which is what av1_copy_and_extend_frame
+ * (av1/encoder/extend.c:113-163) leaves in every lookahead slot; only the crop
+ * area is read from the host, borders are rebuilt on the device. */
+typedef struct {
+  const void *plane[3];
+  int stride[2];     /* y_stride, uv_stride (samples) */
+  int crop_w[2];     /* y_crop_width, uv_crop_width */
+  int crop_h[2];     /* y_crop_height, uv_crop_height */
+  int aligned_w[2];  /* y_width, uv_width   (widths[]: 8-aligned luma size >> ss) */
+  int aligned_h[2];  /* y_height, uv_height */
+  int border;        /* luma border of the host allocation (samples) */
+  int ss_x, ss_y;    /* subsampling_x/y */
+  int is_hbd;        /* flags & YV12_FLAG_HIGHBITDEPTH */
+  uint64_t frame_id; /* lookahead display index (lookahead.h:37): same id => same pixels; 0 = never cache */
+} tf_gpu_frame;
+
+/* Everything av1_tf_do_filtering_row (temporal_filter.c:788-939) and
+ * tf_motion_search (:87-253) read from AV1_COMP, resolved to plain values. */
+typedef struct {
+  int num_frames;        /* tf_ctx.num_frames */
+  int filter_frame_idx;  /* tf_ctx.filter_frame_idx */
+  int num_planes;        /* av1_num_planes(cm): 1 or 3 */
+  int bit_depth;         /* seq_params->bit_depth / mbd->bd: 8, 10, 12 */
+  double noise_levels[3];/* tf_ctx.noise_levels (temporal_filter.c:1023-1027) */
+  int q_factor;          /* av1_get_q(cpi) (:779-786) */
+  int filter_strength;   /* FINAL strength after the psy / key-frame overrides (:813-842) */
+  int mi_rows, mi_cols;  /* cm->mi_params (4-px units of the 8-aligned frame) */
+  int border_in_pixels;  /* oxcf.border_in_pixels (enters av1_set_mv_*_limits, mcomp.h:216-240) */
+  int force_integer_mv;  /* cm->features.cur_frame_force_integer_mv */
+  int allow_hp;          /* cm->features.allow_high_precision_mv */
+  int subpel_method;     /* TF_GPU_SUBPEL_* */
+  int subpel_iters_per_step; /* sf.mv_sf.subpel_iters_per_step */
+  int prune_mesh_level;  /* sf.mv_sf.prune_mesh_search */
+  int mesh_patterns[4][2]; /* sf.mv_sf.mesh_patterns[i].{range,interval} */
+  int use_downsampled_sad; /* sf.mv_sf.use_downsampled_sad */
+  int compute_frame_diff;  /* frame_diff != NULL (:1283) */
+  int out_row_begin, out_row_end; /* slab mode: 32-px block rows [begin,end); 0,0 = all rows */
+  int reserved[8];
+} tf_gpu_params;
+
+/* Per-(block, frame) intermediate state for parity tests (what a debug build of
+ * the reference would dump from av1_tf_do_filtering_row).  All pointers are
+ * optional HOST buffers. */
+typedef struct {
+  int16_t *subblock_mvs;   /* [blocks][num_frames][4][2] (row,col) 1/8 pel */
+  int32_t *subblock_mses;  /* [blocks][num_frames][4] */
+  uint16_t *pred;          /* [blocks][num_frames][num_pels] */
+  uint32_t *accum;         /* [blocks][num_pels] */
+  uint16_t *count;         /* [blocks][num_pels] */
+} tf_gpu_dump;
+
+int tf_gpu_abi_version(void);
+
+/* Replaces nothing in the reference (it has no device): context = one CUDA
+ * device + stream + frame cache.  Analogue of tf_alloc_and_reset_data
+ * (temporal_filter.h:354) hoisted out of the per-call path. */
+int tf_gpu_create(tf_gpu_ctx **ctx, const tf_gpu_device_cfg *cfg);
+void tf_gpu_destroy(tf_gpu_ctx *ctx);
+const char *tf_gpu_last_error(const tf_gpu_ctx *ctx);
+
+/* av1_estimate_noise_from_single_plane (temporal_filter.c:1150-1194), called by
+ * tf_setup_filtering_buffer (:1023-1027) and the key-frame gate
+ * (encode_strategy.c:746-750).  Uploads (and caches) the frame. */
+int tf_gpu_estimate_noise(tf_gpu_ctx *ctx, const tf_gpu_frame *frame, int plane,
+                          int bit_depth, int edge_thresh, double *noise_level);
+
+/* The body of av1_temporal_filter (temporal_filter.c:1294-1311): for every
+ * 32x32 block, motion search + predictor + weighting against each frame of the
+ * window, normalisation into `out`, optional FRAME_DIFF {sum, sse}
+ * (temporal_filter.h:83-86).  Synchronous; host buffers are only used during
+ * the call.  `out` planes receive full blocks (mb_rows*32 x mb_cols*32 luma
+ * samples, as temporal_filter.c:740-777 writes them). */
+int tf_gpu_filter(tf_gpu_ctx *ctx, const tf_gpu_params *params,
+                  const tf_gpu_frame *frames /*[num_frames]*/, tf_gpu_frame *out,
+                  int64_t diff_sum_sse[2] /* nullable */);
+
+/* Same, additionally returning the per-block intermediate state. */
+int tf_gpu_filter_dump(tf_gpu_ctx *ctx, const tf_gpu_params *params,
+                       const tf_gpu_frame *frames, tf_gpu_frame *out,
+                       int64_t diff_sum_sse[2], const tf_gpu_dump *dump);
+
+/* Asynchronous pair for pipelined callers (KF + ARF windows of one GOP are
+ * issued back to back by av1_tf_info_filtering, temporal_filter.c:1358-1377):
+ * submit enqueues upload + kernels + download on the context's stream and
+ * returns a ticket; wait blocks until that ticket's output is in `out`. */
+int tf_gpu_submit(tf_gpu_ctx *ctx, const tf_gpu_params *params,
+                  const tf_gpu_frame *frames, tf_gpu_frame *out,
+                  int64_t diff_sum_sse[2], uint64_t *ticket);
+int tf_gpu_wait(tf_gpu_ctx *ctx, uint64_t ticket);
+
+/* Step before / after the path: upload a source frame
+ * into the device cache when it enters the lookahead (av1_lookahead_push,
+ * lookahead.c:101-163) so that tf_gpu_filter never waits on PCIe; drop it when
+ * it leaves. */
+int tf_gpu_cache_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *frame);
+int tf_gpu_evict_frame(tf_gpu_ctx *ctx, uint64_t frame_id);
+
+/* Device-resident variant used by the benchmark's kernel-only number and by the
+ * multi-GPU slab mode: frames must already be cached (ids), output stays on the
+ * device until tf_gpu_download_output.  time_ms (nullable) receives the CUDA
+ * event time of the filter kernel alone. */
+int tf_gpu_filter_resident(tf_gpu_ctx *ctx, const tf_gpu_params *params,
+                           const uint64_t *frame_ids /*[num_frames]*/,
+                           int64_t diff_sum_sse[2], float *time_ms);
+int tf_gpu_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, int row_begin, int row_end);
+/* Raw device pointer + pitch (bytes) of an output plane, for NCCL gathers in
+ * slab mode (the reference's counterpart is the shared tf_ctx->output_frame
+ * written by all row workers, av1/encoder/ethread.c:2083-2108). */
+int tf_gpu_output_device_plane(tf_gpu_ctx *ctx, int plane, void **dptr, size_t *pitch_bytes,
+                               int *rows, int *row_bytes);
+
+/* Pinned host memory helpers so lookahead buffers can be DMA'd directly. */
+int tf_gpu_host_register(tf_gpu_ctx *ctx, void *ptr, size_t bytes);
+int tf_gpu_host_unregister(tf_gpu_ctx *ctx, void *ptr);
+
+/* Launch statistics of the last filter call: number of kernel launches and the
+ * device time (ms) of the block-filter kernel. */
+int tf_gpu_last_stats(const tf_gpu_ctx *ctx, int *kernel_launches, float *filter_kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TF_GPU_H_ */
