@@ -27,7 +27,8 @@ EXPORTS = [
     "tf_gpu_abi_version", "tf_gpu_create", "tf_gpu_destroy", "tf_gpu_last_error", "tf_gpu_estimate_noise",
     "tf_gpu_filter", "tf_gpu_filter_dump", "tf_gpu_submit", "tf_gpu_wait", "tf_gpu_cache_frame",
     "tf_gpu_evict_frame", "tf_gpu_filter_resident", "tf_gpu_download_output", "tf_gpu_output_device_plane",
-    "tf_gpu_host_register", "tf_gpu_host_unregister", "tf_gpu_last_stats",
+    "tf_gpu_host_register", "tf_gpu_host_unregister", "tf_gpu_last_stats", "tf_gpu_event_record",
+    "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench",
 ]
 
 
@@ -101,6 +102,10 @@ def load_library():
     lib.tf_gpu_host_register.argtypes = [vp, vp, C.c_size_t]
     lib.tf_gpu_host_unregister.argtypes = [vp, vp]
     lib.tf_gpu_last_stats.argtypes = [vp, C.POINTER(i), C.POINTER(C.c_float)]
+    lib.tf_gpu_event_record.argtypes = [vp, i]
+    lib.tf_gpu_event_elapsed_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]
+    lib.tf_gpu_synchronize.argtypes = [vp]
+    lib.tf_gpu_microbench.argtypes = [vp, i, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -296,6 +301,22 @@ class TemporalFilterGpu:
 
     def host_unregister(self, arr):
         self._check(self.lib.tf_gpu_host_unregister(self.h, arr.ctypes.data))
+
+    def event_record(self, slot):
+        self._check(self.lib.tf_gpu_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._check(self.lib.tf_gpu_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        self._check(self.lib.tf_gpu_synchronize(self.h))
+
+    def microbench(self, kind):
+        v = C.c_double()
+        self._check(self.lib.tf_gpu_microbench(self.h, kind, C.byref(v)))
+        return v.value
 
     def last_stats(self):
         n, ms = C.c_int(), C.c_float()

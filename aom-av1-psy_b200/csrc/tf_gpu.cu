@@ -59,6 +59,7 @@ struct tf_gpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t user_ev[4] = { nullptr, nullptr, nullptr, nullptr };
   std::vector<DevFrame> cache;
   DevFrame out;
   uint64_t use_counter = 0, epoch = 0;
@@ -500,6 +501,7 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->user_ev[i]);
   for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->tickets[i].ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_diff, 16 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_diff, 16 * sizeof(unsigned long long));
@@ -539,6 +541,8 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
   if (ctx->h_noise) cudaFreeHost(ctx->h_noise);
   for (int i = 0; i < 8; i++)
     if (ctx->tickets[i].ev) cudaEventDestroy(ctx->tickets[i].ev);
+  for (int i = 0; i < 4; i++)
+    if (ctx->user_ev[i]) cudaEventDestroy(ctx->user_ev[i]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -723,6 +727,59 @@ int tf_gpu_last_stats(const tf_gpu_ctx *ctx, int *kernel_launches, float *filter
   if (!ctx) return TF_GPU_ERR_INVALID;
   if (kernel_launches) *kernel_launches = ctx->last_launches;
   if (filter_kernel_ms) *filter_kernel_ms = ctx->last_kernel_ms;
+  return TF_GPU_OK;
+}
+
+int tf_gpu_event_record(tf_gpu_ctx *ctx, int slot) {
+  if (!ctx || slot < 0 || slot > 3) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->user_ev[slot], ctx->stream));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_event_elapsed_ms(tf_gpu_ctx *ctx, int slot_begin, int slot_end, float *ms) {
+  if (!ctx || !ms || slot_begin < 0 || slot_begin > 3 || slot_end < 0 || slot_end > 3) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(ctx->user_ev[slot_end]));
+  CU(cudaEventElapsedTime(ms, ctx->user_ev[slot_begin], ctx->user_ev[slot_end]));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_synchronize(tf_gpu_ctx *ctx) {
+  if (!ctx) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_microbench(tf_gpu_ctx *ctx, int kind, double *giga_lane_ops_per_s) {
+  if (!ctx || !giga_lane_ops_per_s || kind < 0 || kind > 5) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, ctx->device));
+  unsigned *d_out = nullptr;
+  CU(cudaMalloc(&d_out, 4));
+  const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = kind == 5 ? 2000 : 4000;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    switch (kind) {
+      case 0: microbench_kernel<0><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u + rep); break;
+      case 1: microbench_kernel<1><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u + rep); break;
+      case 2: microbench_kernel<2><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u + rep); break;
+      case 3: microbench_kernel<3><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u + rep); break;
+      case 4: microbench_kernel<4><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u + rep); break;
+      default: microbench_kernel<5><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 12345u + rep); break;
+    }
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaFree(d_out);
+  const double lane_ops = (double)blocks * threads * (double)iters * 64.0;
+  *giga_lane_ops_per_s = lane_ops / (best * 1e-3) / 1e9;
   return TF_GPU_OK;
 }
 

@@ -1132,4 +1132,38 @@ __global__ void noise_kernel(const T *src, int pitch, int width, int height, int
   }
 }
 
+// ---------------------------------------------------------------------------
+// Integer-pipe microbenchmark (roofline denominators).  Eight
+// independent dependency chains per thread, 1024 resident threads per SM.
+// ---------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) microbench_kernel(unsigned *out, int iters, unsigned seed) {
+  unsigned a[8];
+  double d[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u;
+    d[i] = (double)a[i] * 1e-9;
+  }
+  const unsigned b = seed | 0x01010101u;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (KIND == 0) a[i] = a[i] + b + (unsigned)it;                       // IADD3
+        else if (KIND == 1) a[i] = a[i] * b + (unsigned)it;                  // IMAD
+        else if (KIND == 2) a[i] = __vsadu4(a[i] ^ (unsigned)it, b) + a[i];   // VABSDIFF4.ACC (+LOP)
+        else if (KIND == 3) a[i] = __vmaxu2(a[i], b + (unsigned)it);          // VIMNMX.U16x2 (+IADD)
+        else if (KIND == 4) a[i] = __dp4a(a[i], b, a[i]);                     // IDP.4A
+        else d[i] = fma(d[i], 1.0000001, 1e-9);                               // DFMA
+      }
+    }
+  }
+  unsigned acc = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) acc += a[i] + (unsigned)(long long)d[i];
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
 }  // namespace tfk

@@ -1,0 +1,451 @@
+#!/usr/bin/env python3
+"""bench.py -- ARF-filtered frames/s of the B200 temporal filter (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 4k10_n15|1080p10_n11|1080p8_n7]
+                    [--mode windows|slab] [--impl tfgpu|reference]
+
+A step = one pass of the hot path over one ARF window = one filtered output frame
+per GPU (mode windows, weak scaling: independent windows per GPU, no collective) or
+one window sharded by 32-px block rows over all GPUs and gathered with NCCL (mode
+slab, strong scaling).  Prints ONE JSON line (rank 0).
+
+ value     frames/s with the window resident in HBM (device-event time of K steps on the
+           library's own stream, max over ranks)
+ e2e       the same through tf_gpu_filter() with HOST (pinned) buffers: H2D of all window
+           frames + D2H of the filtered frame inside the timed region, every step
+ roofline  HBM view of the block kernel (algorithmic bytes = (N+1) planes per launch) plus
+           the INT view the survey says binds: T_int from measured pipe rates
+ cpu_baseline  the reference's C temporal filter (oracle/_ref, else the oracle port) on a
+           bounded row sample of the same window, 1 core
+
+--impl reference times the reference's own CPU implementation on all host cores (row
+sharding across processes, the reference's own MT axis: av1/encoder/ethread.c:2062-2189).
+"""
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (width, height, bit_depth, num_frames, filter_strength)   SURVEY 8d configs
+    "4k10_n15": (3840, 2160, 10, 15, 5),
+    "1080p10_n11": (1920, 1080, 10, 11, 5),
+    "1080p8_n7": (1920, 1080, 8, 7, 4),
+    "cif8_n7": (352, 288, 8, 7, 5),
+}
+Q_FACTOR = 32  # av1_get_q() of a mid-quality ARF; held fixed so runs are comparable
+
+
+def load_package():
+    name = "aom_av1_psy_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    path = os.path.join(ROOT, "aom-av1-psy_b200", "__init__.py")
+    spec = importlib.util.spec_from_file_location(name, path, submodule_search_locations=[os.path.dirname(path)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_window(width, height, bd, n, seed):
+    import _clips
+    return _clips.moving_texture(width, height, n, bd, seed=seed)
+
+
+def plane_bytes(width, height, bd):
+    es = 2 if bd > 8 else 1
+    return (width * height + 2 * ((width + 1) // 2) * ((height + 1) // 2)) * es
+
+
+# ---------------------------------------------------------------------------------------
+# INT roofline: scalar-equivalent pixel operations per (block, reference frame)
+# ---------------------------------------------------------------------------------------
+def int_work_per_block_ref(allow_hp):
+    sad = 141 * (512 + 4 * 128)              # 1x32x32 + 4x16x16 searches, 141 sites each, skip-row SAD
+    var = 2 * 2048                           # full-pel variance re-scores
+    evals = 5 * (3 if allow_hp else 2) + 1   # sub-pel candidates (PRUNED_MORE, iters 1)
+    subpel = evals * 2048 * 6
+    pred = 4 * (27 * 16 + 16 * 16) * 12 + 8 * (19 * 8 + 8 * 8) * 12
+    weights = 1536 * 29
+    return dict(sad=sad, var=var, subpel=subpel, pred=pred, weights=weights)
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------
+def cpu_filter_class():
+    import _ref
+    if _ref.available():
+        return _ref.RefFilter, "reference"
+    import _oracle
+    return _oracle.OracleFilter, "port"
+
+
+def cpu_baseline(p, frames, rows, mb_rows):
+    """1-core bounded sample: block rows `rows` of the window."""
+    cls, kind = cpu_filter_class()
+    f = cls(p, frames)
+    t = time.perf_counter()
+    f.run(record=False, rows=rows)
+    dt = time.perf_counter() - t
+    f.close()
+    frac = (rows[1] - rows[0]) / mb_rows
+    return {"value": frac / dt, "unit": "frames/s", "cores": 1, "kind": kind,
+            "sample": f"block rows [{rows[0]},{rows[1]}) of {mb_rows} of one window ({dt:.2f} s)"}
+
+
+def _ref_worker(conn, filt):
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
+        t = time.perf_counter()
+        if msg[1] > msg[0]:
+            filt.run(record=False, rows=msg)
+        conn.send(time.perf_counter() - t)
+
+
+def run_reference_arm(args, wl):
+    """The reference's CPU temporal filter on all host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    import _params
+    width, height, bd, n, strength = WORKLOADS[wl]
+    frames = make_window(width, height, bd, n, seed=77 if bd > 8 else 1234)
+    p = _params.tf_params(width, height, n, bit_depth=bd, q_factor=Q_FACTOR, filter_strength=strength)
+    cls, kind = cpu_filter_class()
+    filt = cls(p, frames)
+    p["noise_levels"] = tuple(filt.estimate_noise())
+    filt.close()
+    filt = cls(p, frames)
+    mb_rows = (height + 31) // 32
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # calibrate on one middle row, then size a step to about 3 s of wall time
+    mid = mb_rows // 2
+    t = time.perf_counter()
+    filt.run(record=False, rows=(mid, mid + 1))
+    t_row = time.perf_counter() - t
+    rows_per_step = int(min(mb_rows, max(ncores, 3.0 * ncores / max(t_row, 1e-6))))
+    nw = min(ncores, rows_per_step)
+    ctx = mp.get_context("fork")
+    workers = []
+    for _ in range(nw):
+        a, b = ctx.Pipe()
+        pr = ctx.Process(target=_ref_worker, args=(b, filt), daemon=True)
+        pr.start()
+        workers.append((pr, a))
+    r0 = max(0, (mb_rows - rows_per_step) // 2)
+    bounds = [r0 + (rows_per_step * i) // nw for i in range(nw + 1)]
+
+    def step():
+        t0 = time.perf_counter()
+        for i, (_, c) in enumerate(workers):
+            c.send((bounds[i], bounds[i + 1]))
+        for _, c in workers:
+            c.recv()
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    for pr, c in workers:
+        c.send(None)
+    for pr, _ in workers:
+        pr.join(timeout=5)
+    total = sum(times)
+    frac = rows_per_step / mb_rows
+    value = frac * args.steps / total
+    sample = f"block rows [{r0},{r0 + rows_per_step}) of {mb_rows} per step, sharded over {nw} processes"
+    line = {
+        "impl": "reference", "metric": "arf_filtered_frames_per_sec", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps / frac,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16" if bd > 8 else "u8", "data": "synthetic",
+        "config": {"workload": wl, "width": width, "height": height, "bit_depth": bd, "num_frames": n,
+                   "speed_class": "good cpu-used=4", "note": "ms_per_step is per whole frame (sample time / sampled fraction)"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": nw, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="4k10_n15", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="windows", choices=["windows", "slab"])
+    ap.add_argument("--impl", default="tfgpu", choices=["tfgpu", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "tfgpu" else args.warmup
+    wl = args.workload
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import _params
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the temporal filter has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    pkg = load_package()
+    ctx = pkg.TemporalFilterGpu(device=local, max_cached_frames=40)
+
+    width, height, bd, n, strength = WORKLOADS[wl]
+    use_hbd = bd > 8
+    mb_rows, mb_cols = (height + 31) // 32, (width + 31) // 32
+    p = _params.tf_params(width, height, n, bit_depth=bd, q_factor=Q_FACTOR, filter_strength=strength)
+
+    # windows resident on this GPU: enough distinct data to exceed L2 (126 MB) several times
+    win_bytes = plane_bytes(width, height, bd) * n
+    nwin = max(2, int(np.ceil(400e6 / win_bytes)))
+    nwin = min(nwin, 40 // n) if 40 // n >= 1 else 1
+    slab = args.mode == "slab" and world > 1
+    windows = []
+    for w in range(nwin):
+        seed = (77 if bd > 8 else 1234) + (0 if slab else 1000 * rank) + w
+        frames = make_window(width, height, bd, n, seed)
+        bufs = []
+        for i, (y, u, v) in enumerate(frames):
+            b = pkg.Yv12Buffer(width, height, 1, 1, use_hbd, p["border"], frame_id=1 + w * 100 + i)
+            b.set_planes(y, u, v, extend=False)
+            for a in b.alloc:
+                ctx.host_register(a)
+            bufs.append(b)
+        windows.append((frames, bufs))
+    out = pkg.Yv12Buffer(width, height, 1, 1, use_hbd, p["border"])
+    for a in out.alloc:
+        ctx.host_register(a)
+
+    # noise levels of the frame to filter (tf_setup_filtering_buffer, temporal_filter.c:1023-1027)
+    fi = p["filter_frame_idx"]
+    p["noise_levels"] = tuple(ctx.estimate_noise_from_single_plane(windows[0][1][fi], pl, bd) for pl in range(3))
+    for _, bufs in windows:
+        for b in bufs:
+            ctx.cache_frame(b)
+
+    if slab:
+        r0 = (mb_rows * rank) // world
+        r1 = (mb_rows * (rank + 1)) // world
+        p["out_row_begin"], p["out_row_end"] = r0, r1
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    gather_bufs = None
+
+    def slab_gather(diff):
+        """NCCL gather of the disjoint output row slabs to rank 0 and a 16-byte all-reduce of
+        FRAME_DIFF (integer sums, so order independent like ethread.c:2161-2173)."""
+        nonlocal gather_bufs
+        max_rows = max((mb_rows * (r + 1)) // world - (mb_rows * r) // world for r in range(world))
+        tensors = []
+        for pl in range(3):
+            ptr, pitch, rows, row_bytes = ctx.output_device_plane(pl)
+            bh = 32 >> (1 if pl else 0)
+
+            class _W:  # zero-copy view of the library's output plane (one spare block row fits the device border)
+                pass
+            wobj = _W()
+            wobj.__cuda_array_interface__ = {"shape": ((mb_rows + 1) * bh * pitch,), "typestr": "|u1",
+                                             "data": (ptr, False), "version": 3}
+            t = torch.as_tensor(wobj, device=f"cuda:{local}")
+            lo = (mb_rows * rank) // world * bh * pitch
+            tensors.append(t[lo:lo + max_rows * bh * pitch])
+        if gather_bufs is None:
+            gather_bufs = [[torch.empty_like(t) for _ in range(world)] if rank == 0 else None for t in tensors]
+        for t, g in zip(tensors, gather_bufs):
+            dist.gather(t, g, dst=0)
+        d = torch.from_numpy(diff.copy()).to(f"cuda:{local}")
+        dist.all_reduce(d)
+        torch.cuda.current_stream().synchronize()
+
+    ids = [[b.frame_id for b in bufs] for _, bufs in windows]
+    launches = 0
+
+    def step(k):
+        nonlocal launches
+        ms, diff = ctx.filter_resident(p, ids[k % nwin])
+        launches += ctx.last_stats()[0]
+        if slab:
+            slab_gather(diff)
+        return ms
+
+    for k in range(args.warmup):
+        step(k)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches = 0
+    ctx.event_record(0)
+    t0 = time.perf_counter()
+    kernel_ms = 0.0
+    for k in range(args.steps):
+        kernel_ms += step(k)
+    ctx.event_record(1)
+    dev_ms = ctx.event_elapsed_ms(0, 1)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    step_ms = max(dev_ms, wall_ms if slab else dev_ms)  # slab mode includes the NCCL gather (other stream)
+    tmax = torch.tensor([step_ms, kernel_ms], device=f"cuda:{local}", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tot_ms, kern_ms_max = tmax.tolist()
+    frames_done = args.steps * (1 if slab else world)
+    value = frames_done / (tot_ms * 1e-3)
+
+    # ---- e2e: host buffers through tf_gpu_filter, copies inside the timed region --------
+    e2e = None
+    if not args.no_e2e and not slab:
+        for _, bufs in windows:
+            for b in bufs:
+                b.frame_id = 0  # never cached: every step uploads the whole window
+        for k in range(2):
+            ctx.temporal_filter(p, windows[k % nwin][1], out)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            ctx.temporal_filter(p, windows[k % nwin][1], out)
+        barrier()
+        e_ms = (time.perf_counter() - t0) * 1e3
+        te = torch.tensor([e_ms], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        es = 2 if use_hbd else 1
+        d2h = sum(out.full_blocks(pl).size for pl in range(3)) * es
+        e2e = {"value": args.steps * world / (te.item() * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": plane_bytes(width, height, bd) * n, "d2h_bytes_per_step": int(d2h)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline ---------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    rows_frac = ((p["out_row_end"] - p["out_row_begin"]) / mb_rows) if slab else 1.0
+    alg_bytes = (n + 1) * plane_bytes(width, height, bd) * rows_frac
+    kern_s = kern_ms_max * 1e-3 / args.steps
+    achieved = alg_bytes / kern_s / 1e9
+    rates = {k: ctx.microbench(i) for i, k in enumerate(["iadd3", "imad", "vabsdiff4", "vimnmx_u16x2", "idp4a", "dfma"])}
+    W = int_work_per_block_ref(p["allow_hp"])
+    r_sad = rates["vabsdiff4"] * 4 if bd == 8 else rates["vimnmx_u16x2"] * 2 / 2  # px per lane-instruction
+    t_int_block = (W["sad"] / r_sad + (W["var"] + W["subpel"] + W["pred"]) / rates["imad"] + W["weights"] / rates["iadd3"]) / 1e9
+    t_int = t_int_block * mb_rows * mb_cols * (n - 1) * rows_frac
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "traffic": None, "peak_source": peak_src, "kernel": "tf_block_kernel", "kernel_ms": kern_s * 1e3,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "int": {"note": "binding roofline per SURVEY 8d: T_int = sum_class W_class / R_class over measured pipe rates",
+                "work_per_block_ref": W, "rates_giga_lane_ops_per_s": rates, "t_int_ms": t_int * 1e3,
+                "frac": t_int / kern_s},
+    }
+
+    line = {
+        "metric": "arf_filtered_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if slab else "weak", "vs_baseline": None, "dtype": "u16" if use_hbd else "u8",
+        "data": "synthetic",
+        "config": {"workload": wl, "width": width, "height": height, "bit_depth": bd, "chroma": "4:2:0",
+                   "num_frames": n, "filter_strength": strength, "q_factor": Q_FACTOR,
+                   "speed_class": "good cpu-used=4 (PRUNED_MORE, prune mesh lvl2, skip-row SAD)",
+                   "mode": "slab rows + NCCL gather" if slab else "independent windows per GPU",
+                   "l2": f"inputs larger than L2: {nwin} resident windows x {win_bytes / 1e6:.0f} MB cycled",
+                   "timing": "CUDA events on the library stream around K steps, max over ranks"},
+        "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        mid = mb_rows // 2
+        nrows = 4 if width >= 3000 else (8 if width >= 1900 else mb_rows)
+        rows = (max(0, mid - nrows // 2), min(mb_rows, mid - nrows // 2 + nrows))
+        pc = dict(p)
+        pc["out_row_begin"] = pc["out_row_end"] = 0
+        line["cpu_baseline"] = cpu_baseline(pc, windows[0][0], rows, mb_rows)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

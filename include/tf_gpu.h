@@ -172,6 +172,17 @@ int tf_gpu_host_unregister(tf_gpu_ctx *ctx, void *ptr);
  * device time (ms) of the block-filter kernel. */
 int tf_gpu_last_stats(const tf_gpu_ctx *ctx, int *kernel_launches, float *filter_kernel_ms);
 
+/* Measurement hooks (bench.py): CUDA events recorded on the context's own
+ * stream (the stream every kernel of this library is launched on), slots 0..3. */
+int tf_gpu_event_record(tf_gpu_ctx *ctx, int slot);
+int tf_gpu_event_elapsed_ms(tf_gpu_ctx *ctx, int slot_begin, int slot_end, float *ms);
+int tf_gpu_synchronize(tf_gpu_ctx *ctx);
+/* Integer-pipe microbenchmark used for the INT roofline denominator
+ * (SURVEY 8d): kind 0 = IADD3 (alu pipe), 1 = IMAD (fma pipe),
+ * 2 = VABSDIFF4.U8.ACC, 3 = VIMNMX.U16x2, 4 = IDP.4A, 5 = DFMA (fp64).
+ * Returns giga warp-lane instructions per second over the whole chip. */
+int tf_gpu_microbench(tf_gpu_ctx *ctx, int kind, double *giga_lane_ops_per_s);
+
 #ifdef __cplusplus
 }
 #endif
