@@ -26,7 +26,7 @@ using namespace tfk;
 
 namespace {
 
-constexpr int DEV_BORDER = 64;  // luma device border (samples); see DESIGN.md "Data layout"
+constexpr int DEV_BORDER = 80;  // luma device border (samples); see DESIGN.md "Data layout"
 
 struct Geometry {
   int is_hbd, ss_x, ss_y, num_planes;
@@ -117,7 +117,7 @@ bool make_geometry(const tf_gpu_frame *f, int num_planes, Geometry *g) {
     g->bx[k] = k ? DEV_BORDER >> f->ss_x : DEV_BORDER;
     g->by[k] = k ? DEV_BORDER >> f->ss_y : DEV_BORDER;
     g->pitch[k] = align_up(g->aligned_w[k] + 2 * g->bx[k], 128);
-    g->rows[k] = g->aligned_h[k] + 2 * g->by[k];
+    g->rows[k] = g->aligned_h[k] + 2 * g->by[k] + 2;  // + slack rows: window / word over-reads stay inside
   }
   return true;
 }

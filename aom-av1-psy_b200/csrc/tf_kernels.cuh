@@ -111,7 +111,17 @@ struct Search {
   int sad_lambda, sse_lambda;
   int hbd_shift;
   int is_hbd;
+  // Shared-memory search window: the reference samples needed by every
+  // candidate whose full-pel MV lies within +-wR of (wr, wc).  Candidates inside
+  // are read from shared memory (one conflict-free wavefront per load), the rest
+  // from global memory through L1.
+  unsigned char *win;  // nullptr = no window
+  int wr, wc, wR;
+  int wpitch;  // bytes; wpitch/4 is odd
+  int wshift;  // bytes the window origin was aligned down by
 };
+
+constexpr int WIN_BYTES = 12288;  // window capacity per warp (aliases sq | lsum | pred | im)
 
 // SAD lane layout: a candidate occupies LPC lanes (one block row per lane, every
 // other row with skip-row SAD, aom_dsp/sad.c:66-70), so a pass evaluates
@@ -123,7 +133,48 @@ struct SadL {
   static constexpr int CPP = 32 / LPC;
   static constexpr int NW = W * (int)sizeof(T) / 4;
   static constexpr int RSTEP = SKIP ? 2 : 1;
+  static constexpr int MAXP = 12 / CPP;  // passes for a 12-site stage
 };
+
+// Largest window radius that fits WIN_BYTES for a W x W block of T.
+template <typename T, int W>
+struct WinCfg {
+  static constexpr int R = (W == 32) ? 16 : 24;
+  static constexpr int ROWS = W + 2 * R;
+  static constexpr int ROWB = ((W + 2 * R) * (int)sizeof(T) + 15 + 15) / 16 * 16;  // + align-down slack, 16B chunks
+  static constexpr int PITCH = ROWB + 4 + ((((ROWB + 4) / 4) & 1) ? 0 : 4);         // words per row odd
+  static_assert(ROWS * PITCH <= WIN_BYTES, "search window does not fit");
+};
+
+// Cooperative, coalesced window fill: 16-byte global loads, 4-byte shared stores.
+template <typename T, int W>
+__device__ __noinline__ void window_load(Search<T> &S, unsigned char *buf, int wr, int wc) {
+  using C = WinCfg<T, W>;
+  const int lane = lane_id();
+  const T *g0 = S.ref + (wr - C::R) * S.stride + (wc - C::R);
+  const uintptr_t a = reinterpret_cast<uintptr_t>(g0);
+  const int shift = (int)(a & 15);
+  const unsigned char *ga = reinterpret_cast<const unsigned char *>(a - shift);
+  constexpr int CPR = C::ROWB / 16;  // chunks per row
+  const size_t gpitch = (size_t)S.stride * sizeof(T);
+  __syncwarp();
+  for (int q = lane; q < C::ROWS * CPR; q += 32) {
+    const int row = q / CPR, ch = q - row * CPR;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ga + row * gpitch + ch * 16));
+    uint32_t *d = reinterpret_cast<uint32_t *>(buf + row * C::PITCH + ch * 16);
+    d[0] = v.x;
+    d[1] = v.y;
+    d[2] = v.z;
+    d[3] = v.w;
+  }
+  __syncwarp();
+  S.win = buf;
+  S.wr = wr;
+  S.wc = wc;
+  S.wR = C::R;
+  S.wpitch = C::PITCH;
+  S.wshift = shift;
+}
 
 template <typename T, int W, bool SKIP>
 __device__ __forceinline__ void sad_load_src(const T *src, int stride, uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
@@ -140,20 +191,43 @@ __device__ __forceinline__ void sad_load_src(const T *src, int stride, uint32_t 
   }
 }
 
-// Partial SAD of this lane's row of the candidate at full-pel (r, c).
+// Where the candidates of one diamond stage / mesh level are read from: the
+// shared-memory window or global memory.  Uniform per stage, so there is a single
+// code path (generic loads) and no per-candidate test.
+struct SadSrc {
+  const unsigned char *base;  // address of the sample at full-pel MV (0, 0), row 0
+  int pitchB;                 // bytes per row
+};
+template <typename T>
+__device__ __forceinline__ SadSrc sad_src(const Search<T> &S, bool use_window) {
+  SadSrc q;
+  if (use_window) {
+    q.base = S.win + ((S.wR - S.wr) * S.wpitch + (S.wR - S.wc) * (int)sizeof(T) + S.wshift);
+    q.pitchB = S.wpitch;
+  } else {
+    q.base = reinterpret_cast<const unsigned char *>(S.ref);
+    q.pitchB = S.stride * (int)sizeof(T);
+  }
+  return q;
+}
+// All MVs within +-reach of (r, c) lie inside the window.
+template <typename T>
+__device__ __forceinline__ bool window_covers(const Search<T> &S, int r, int c, int reach) {
+  return S.win != nullptr && iabs(r - S.wr) + reach <= S.wR && iabs(c - S.wc) + reach <= S.wR;
+}
+
+// Partial SAD of this lane's row (row = lane's block row) of the candidate at full-pel (r, c).
 template <typename T, int W, bool SKIP>
-__device__ __forceinline__ unsigned sad_partial(const T *ref, int stride, int r, int c, bool valid,
-                                                const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+__device__ __forceinline__ unsigned sad_partial(const SadSrc &Q, const unsigned char *safe, int r, int c, int row,
+                                                bool valid, const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
   using L = SadL<T, W, SKIP>;
-  if (!valid) return 0u;
-  const int row = (lane_id() % L::LPC) * L::RSTEP;
-  const T *p = ref + (r + row) * stride + c;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const unsigned char *pb = valid ? Q.base + (r + row) * Q.pitchB + c * (int)sizeof(T) : safe;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(pb);
   const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
   const unsigned sh = (unsigned)(a & 3) * 8;
   uint32_t w[L::NW + 1];
 #pragma unroll
-  for (int j = 0; j <= L::NW; j++) w[j] = __ldg(wp + j);
+  for (int j = 0; j <= L::NW; j++) w[j] = wp[j];
   unsigned s = 0;
   if (sizeof(T) == 1) {
 #pragma unroll
@@ -191,13 +265,21 @@ __device__ __forceinline__ unsigned sad_post(unsigned s, int hbd_shift) {
 
 // SAD of one candidate, result in all lanes.
 template <typename T, int W, bool SKIP>
-__device__ __forceinline__ unsigned sad_single(const Search<T> &S, int r, int c,
+__device__ __forceinline__ unsigned sad_single(const Search<T> &S, int r, int c, int lane,
                                                const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
   using L = SadL<T, W, SKIP>;
-  unsigned part = sad_partial<T, W, SKIP>(S.ref, S.stride, r, c, lane_id() < L::LPC, sw);
+  const SadSrc Q = sad_src(S, window_covers(S, r, c, 0));
+  unsigned part = sad_partial<T, W, SKIP>(Q, reinterpret_cast<const unsigned char *>(S.src), r, c,
+                                          (lane % L::LPC) * L::RSTEP, true, sw);
   part = seg_reduce_u32<L::LPC>(part);
-  part = __shfl_sync(FULL, part, 0);
   return sad_post<SKIP>(part, S.hbd_shift);
+}
+
+template <int FROM>
+__device__ __forceinline__ unsigned group_min_u32(unsigned v) {  // min across lane groups of FROM lanes
+#pragma unroll
+  for (int o = FROM; o < 32; o <<= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+  return v;
 }
 
 // ---------------------------------------------------------------------------
@@ -220,8 +302,8 @@ __device__ __forceinline__ unsigned var_finish(int sum, unsigned long long sse, 
 }
 
 template <typename T, int W>
-__device__ __forceinline__ unsigned variance(const T *a, int as, const T *b, int bs, int hbd_shift,
-                                             unsigned *sse_out) {
+__device__ __noinline__ unsigned variance(const T *a, int as, const T *b, int bs, int hbd_shift,
+                                          unsigned *sse_out) {
   const int lane = lane_id();
   constexpr int RP = 32 / W;  // rows per iteration
   const int col = lane % W, r0 = lane / W;
@@ -247,92 +329,119 @@ __device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
 }
 
 // ---------------------------------------------------------------------------
-// diamond_search_sad (mcomp.c:1299-1416)
+// diamond_search_sad (mcomp.c:1299-1416).  Kept out of line (one copy per
+// layout) so the kernel stays inside the instruction cache.
+//
+// The reference walks the sites of a stage in index order with a running
+// threshold: accept iff sad + cost < bestsad (strict).  Because cost >= 0 the
+// inner "sad < bestsad" pre-test is redundant, so the stage result is the
+// arg-min of (sad + cost) with ties going to the lowest site index, accepted
+// iff it beats the incumbent.  That is evaluated here as a warp min-reduction
+// over keys (total << 4 | site index): bit-exact, and without any sequential
+// per-candidate code.
 // ---------------------------------------------------------------------------
 template <typename T, int W, bool SKIP>
-__device__ unsigned diamond_search(const Search<T> &S, MV2 start, int search_step, int *num00, MV2 *best_mv,
-                                   const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+__device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start, int search_step, int *num00,
+                                                MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
+  constexpr int PU = L::MAXP < 3 ? L::MAXP : 3;  // passes whose loads are issued back to back
+  const Search<T> S = S_in;
   const int lane = lane_id();
+  const int grp = lane / L::LPC, row = (lane % L::LPC) * L::RSTEP;
+  const unsigned char *safe = reinterpret_cast<const unsigned char *>(S.src);
+  uint32_t sw[L::NW];
+  sad_load_src<T, W, SKIP>(S.src, S.stride, sw);
   start.col = iclamp(start.col, S.lim.col_min, S.lim.col_max);
   start.row = iclamp(start.row, S.lim.row_min, S.lim.row_max);
   const int tot_steps = 15 - search_step;
-  *num00 = 0;
-  *best_mv = start;
-  unsigned bestsad = sad_single<T, W, SKIP>(S, start.row, start.col, sw) + sad_cost(S, start.row, start.col);
+  int n00 = 0;
+  MV2 best = start;
+  unsigned bestsad = sad_single<T, W, SKIP>(S, start.row, start.col, lane, sw) + sad_cost(S, start.row, start.col);
   int is_off_center = 0;
   int next_step_size = tot_steps > 2 ? c_sites.radius[tot_steps - 2] : 1;
   for (int step = tot_steps - 1; step >= 0; --step) {
-    int best_site = 0;
     if (step > 0) next_step_size = c_sites.radius[step - 1];
     const int nsites = c_sites.n[step];
     const int rad = c_sites.radius[step];
     // all_in tests only the four axis sites (mcomp.c:1339-1344)
-    const bool all_in = (best_mv->row - rad >= S.lim.row_min) && (best_mv->row + rad <= S.lim.row_max) &&
-                        (best_mv->col - rad >= S.lim.col_min) && (best_mv->col + rad <= S.lim.col_max);
-    for (int idx0 = 1; idx0 <= nsites; idx0 += L::CPP) {
-      const int my_idx = idx0 + lane / L::LPC;
-      int my_r = 0, my_c = 0;
-      bool valid = my_idx <= nsites;
-      if (valid) {
-        my_r = best_mv->row + c_sites.r[step][my_idx];
-        my_c = best_mv->col + c_sites.c[step][my_idx];
-        valid = all_in || in_range(S.lim, my_r, my_c);
-      }
-      unsigned tot = sad_partial<T, W, SKIP>(S.ref, S.stride, my_r, my_c, valid, sw);
-      tot = seg_reduce_u32<L::LPC>(tot);
+    const bool all_in = (best.row - rad >= S.lim.row_min) && (best.row + rad <= S.lim.row_max) &&
+                        (best.col - rad >= S.lim.col_min) && (best.col + rad <= S.lim.col_max);
+    const SadSrc Q = sad_src(S, window_covers(S, best.row, best.col, rad));
+    unsigned mykey = 0xffffffffu;
+#pragma unroll 1
+    for (int p0 = 0; p0 * L::CPP < nsites; p0 += PU) {
+      unsigned part[PU];
+      int cost[PU];
+      bool ok[PU];
 #pragma unroll
-      for (int k = 0; k < L::CPP; k++) {
-        const int idx = idx0 + k;
-        const unsigned t = __shfl_sync(FULL, tot, k * L::LPC);
-        const int cr = __shfl_sync(FULL, my_r, k * L::LPC);
-        const int cc = __shfl_sync(FULL, my_c, k * L::LPC);
-        const int v = __shfl_sync(FULL, (int)valid, k * L::LPC);
-        if (idx <= nsites && v) {
-          unsigned thissad = sad_post<SKIP>(t, S.hbd_shift);
-          if (thissad < bestsad) {
-            thissad += sad_cost(S, cr, cc);
-            if (thissad < bestsad) {
-              bestsad = thissad;
-              best_site = idx;
-            }
-          }
-        }
+      for (int u = 0; u < PU; u++) {  // independent loads + partial SADs
+        const int idx = 1 + (p0 + u) * L::CPP + grp;
+        const bool live = idx <= nsites;
+        const int my_r = best.row + c_sites.r[step][live ? idx : 0];
+        const int my_c = best.col + c_sites.c[step][live ? idx : 0];
+        ok[u] = live && (all_in || in_range(S.lim, my_r, my_c));
+        cost[u] = sad_cost(S, my_r, my_c);
+        part[u] = sad_partial<T, W, SKIP>(Q, safe, my_r, my_c, row, ok[u], sw);
       }
+#pragma unroll
+      for (int u = 0; u < PU; u++) {
+        const unsigned tot = sad_post<SKIP>(seg_reduce_u32<L::LPC>(part[u]), S.hbd_shift) + (unsigned)cost[u];
+        const unsigned key = (tot << 4) | (unsigned)(1 + (p0 + u) * L::CPP + grp);
+        mykey = min(mykey, ok[u] ? key : 0xffffffffu);
+      }
+    }
+    mykey = group_min_u32<L::LPC>(mykey);
+    int best_site = 0;
+    if ((mykey >> 4) < bestsad) {
+      bestsad = mykey >> 4;
+      best_site = (int)(mykey & 15u);
     }
     if (best_site != 0) {
-      best_mv->row += c_sites.r[step][best_site];
-      best_mv->col += c_sites.c[step][best_site];
+      best.row += c_sites.r[step][best_site];
+      best.col += c_sites.c[step][best_site];
       is_off_center = 1;
     }
-    if (is_off_center == 0) (*num00)++;
+    if (is_off_center == 0) n00++;
     if (best_site == 0) {
       while (next_step_size == c_sites.radius[step] && step > 2) {
-        ++(*num00);
+        ++n00;
         --step;
         next_step_size = c_sites.radius[step - 1];
       }
     }
   }
+  *num00 = n00;
+  *best_out = best;
   return bestsad;
 }
 
 // full_pixel_diamond (mcomp.c:1421-1470), cost_list == NULL
 template <typename T, int W, bool SKIP>
-__device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param, MV2 *best_mv,
-                                  const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
-  int n, num00 = 0;
-  int bestsme = (int)diamond_search<T, W, SKIP>(S, start, step_param, &n, best_mv, sw);
-  if (bestsme < INT_MAX_) bestsme = var_cost<T, W>(S, best_mv->row, best_mv->col);
+__device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param, MV2 *best_mv) {
+  int n = 0, num00 = 0;
+  int bestsme = 0;
   const int further_steps = 15 - 1 - step_param;
-  while (n < further_steps) {
-    ++n;
-    if (num00) {
-      num00--;
+  // first pass (pass_n = 0) and the refinement passes share one call site
+  bool first = true;
+  while (first || n < further_steps) {
+    if (!first) {
+      ++n;
+      if (num00) {
+        num00--;
+        continue;
+      }
+    }
+    MV2 tmp;
+    int nn;
+    int thissme = (int)diamond_search<T, W, SKIP>(S, start, step_param + (first ? 0 : n), &nn, &tmp);
+    if (thissme < INT_MAX_) thissme = var_cost<T, W>(S, tmp.row, tmp.col);
+    if (first) {
+      n = nn;
+      bestsme = thissme;
+      *best_mv = tmp;
+      first = false;
     } else {
-      MV2 tmp;
-      int thissme = (int)diamond_search<T, W, SKIP>(S, start, step_param + n, &num00, &tmp, sw);
-      if (thissme < INT_MAX_) thissme = var_cost<T, W>(S, tmp.row, tmp.col);
+      num00 = nn;
       if (thissme < bestsme) {
         bestsme = thissme;
         *best_mv = tmp;
@@ -345,19 +454,29 @@ __device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param,
 // exhaustive_mesh_search (mcomp.c:1474-1543).  The visiting order is the
 // reference's (row major; with step == 1 the 4-wide groups and the tail quirk
 // that never visits end_col unless the column count is a multiple of 4).
+// update_mvs_and_sad (:839-858) is a running strict minimum of sad + cost in
+// visiting order = arg-min with ties to the earliest visit, so every lane
+// group keeps the best key (total << 32 | visit index) of the candidates it
+// evaluated and one warp min-reduction at the end picks the winner.
 template <typename T, int W, bool SKIP>
-__device__ int mesh_search(const Search<T> &S, MV2 start, int range, int step, MV2 *best_mv,
-                           const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+__device__ __noinline__ int mesh_search(const Search<T> &S_in, MV2 start, int range, int step, MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
+  constexpr int PU = 2;
+  const Search<T> S = S_in;
   const int lane = lane_id();
+  const int grp = lane / L::LPC, row = (lane % L::LPC) * L::RSTEP;
+  const unsigned char *safe = reinterpret_cast<const unsigned char *>(S.src);
+  uint32_t sw[L::NW];
+  sad_load_src<T, W, SKIP>(S.src, S.stride, sw);
   start.col = iclamp(start.col, S.lim.col_min, S.lim.col_max);
   start.row = iclamp(start.row, S.lim.row_min, S.lim.row_max);
-  *best_mv = start;
-  unsigned best_sad = sad_single<T, W, SKIP>(S, start.row, start.col, sw) + sad_cost(S, start.row, start.col);
+  MV2 best = start;
+  unsigned best_sad = sad_single<T, W, SKIP>(S, start.row, start.col, lane, sw) + sad_cost(S, start.row, start.col);
   const int start_row = imax(-range, S.lim.row_min - start.row);
   const int start_col = imax(-range, S.lim.col_min - start.col);
   const int end_row = imin(range, S.lim.row_max - start.row);
   const int end_col = imin(range, S.lim.col_max - start.col);
+  *best_out = best;
   if (end_row < start_row || end_col < start_col) return (int)best_sad;
   const int n_rows = (end_row - start_row) / step + 1;
   int n_cols;
@@ -368,42 +487,49 @@ __device__ int mesh_search(const Search<T> &S, MV2 start, int range, int step, M
     n_cols = (ncols % 4 == 0) ? ncols : ncols - 1;
   }
   const int total = n_rows * n_cols;
-  for (int q0 = 0; q0 < total; q0 += L::CPP) {
-    const int q = q0 + lane / L::LPC;
-    const bool valid = q < total;
-    int my_r = 0, my_c = 0;
-    if (valid) {
-      const int ri = q / n_cols, ci = q - ri * n_cols;
-      my_r = start.row + start_row + ri * step;
-      my_c = start.col + start_col + ci * step;
-    }
-    unsigned tot = sad_partial<T, W, SKIP>(S.ref, S.stride, my_r, my_c, valid, sw);
-    tot = seg_reduce_u32<L::LPC>(tot);
+  const SadSrc Q = sad_src(S, window_covers(S, start.row, start.col, range));
+  unsigned long long mykey = ~0ull;
+#pragma unroll 1
+  for (int q0 = 0; q0 < total; q0 += L::CPP * PU) {
+    unsigned part[PU];
+    int cost[PU];
 #pragma unroll
-    for (int k = 0; k < L::CPP; k++) {
-      const unsigned t = __shfl_sync(FULL, tot, k * L::LPC);
-      const int cr = __shfl_sync(FULL, my_r, k * L::LPC);
-      const int cc = __shfl_sync(FULL, my_c, k * L::LPC);
-      if (q0 + k < total) {
-        const unsigned this_sad = sad_post<SKIP>(t, S.hbd_shift);
-        if (this_sad < best_sad) {  // update_mvs_and_sad mcomp.c:839-858
-          const unsigned sad = this_sad + sad_cost(S, cr, cc);
-          if (sad < best_sad) {
-            best_sad = sad;
-            best_mv->row = cr;
-            best_mv->col = cc;
-          }
-        }
-      }
+    for (int u = 0; u < PU; u++) {
+      const int q = q0 + u * L::CPP + grp;
+      const bool valid = q < total;
+      const int qq = valid ? q : 0;
+      const int ri = qq / n_cols, ci = qq - ri * n_cols;
+      const int my_r = start.row + start_row + ri * step, my_c = start.col + start_col + ci * step;
+      cost[u] = sad_cost(S, my_r, my_c);
+      part[u] = sad_partial<T, W, SKIP>(Q, safe, my_r, my_c, row, valid, sw);
+    }
+#pragma unroll
+    for (int u = 0; u < PU; u++) {
+      const int q = q0 + u * L::CPP + grp;
+      const unsigned tot = sad_post<SKIP>(seg_reduce_u32<L::LPC>(part[u]), S.hbd_shift) + (unsigned)cost[u];
+      const unsigned long long key = ((unsigned long long)tot << 32) | (unsigned)q;
+      mykey = (q < total && key < mykey) ? key : mykey;
     }
   }
+#pragma unroll
+  for (int o = L::LPC; o < 32; o <<= 1) {
+    const unsigned long long other = __shfl_xor_sync(FULL, mykey, o);
+    mykey = other < mykey ? other : mykey;
+  }
+  if ((unsigned)(mykey >> 32) < best_sad) {
+    best_sad = (unsigned)(mykey >> 32);
+    const int q = (int)(mykey & 0xffffffffull);
+    const int ri = q / n_cols;
+    best.row = start.row + start_row + ri * step;
+    best.col = start.col + start_col + (q - ri * n_cols) * step;
+  }
+  *best_out = best;
   return (int)best_sad;
 }
 
 // full_pixel_exhaustive (mcomp.c:1547-1617)
 template <typename T, int W, bool SKIP>
-__device__ int full_pixel_exhaustive(const Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv,
-                                     const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+__device__ int full_pixel_exhaustive(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv, unsigned char *winbuf) {
   int interval = P.mesh[0][1], range = P.mesh[0][0];
   *best_mv = start;
   if (range < 7 || range > 256 || interval < 1 || interval > range) return INT_MAX_;
@@ -411,12 +537,19 @@ __device__ int full_pixel_exhaustive(const Search<T> &S, const KParams &P, MV2 s
   range = imax(range, (5 * imax(iabs(best_mv->row), iabs(best_mv->col))) / 4);
   range = imin(range, 256);
   interval = imax(interval, range / baseline_interval_divisor);
-  int bestsme = mesh_search<T, W, SKIP>(S, *best_mv, range, interval, best_mv, sw);
-  if (interval > 1 && range > 7) {
-    for (int i = 1; i < 4; ++i) {
-      bestsme = mesh_search<T, W, SKIP>(S, *best_mv, P.mesh[i][0], P.mesh[i][1], best_mv, sw);
-      if (P.mesh[i][1] == 1) break;
+  int bestsme = 0;
+  for (int i = 0; i < 4; ++i) {  // pass 0, then patterns 1.. until an interval-1 pattern has run
+    if (i > 0) {
+      range = P.mesh[i][0];
+      interval = P.mesh[i][1];
     }
+    MV2 nb;
+    if (!window_covers(S, best_mv->row, best_mv->col, range) && range <= WinCfg<T, W>::R)
+      window_load<T, W>(S, winbuf, best_mv->row, best_mv->col);
+    bestsme = mesh_search<T, W, SKIP>(S, *best_mv, range, interval, &nb);
+    *best_mv = nb;
+    if (i == 0 && !(interval > 1 && range > 7)) break;
+    if (i > 0 && P.mesh[i][1] == 1) break;
   }
   if (bestsme < INT_MAX_) bestsme = var_cost<T, W>(S, best_mv->row, best_mv->col);
   return bestsme;
@@ -426,11 +559,10 @@ __device__ int full_pixel_exhaustive(const Search<T> &S, const KParams &P, MV2 s
 // Returns 1 when the skip-row result must be discarded and the search redone
 // with full SAD (mcomp.c:1777-1810).
 template <typename T, int W, bool SKIP>
-__device__ int full_pixel_search_pass(const Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv) {
-  uint32_t sw[SadL<T, W, SKIP>::NW];
-  sad_load_src<T, W, SKIP>(S.src, S.stride, sw);
+__device__ __noinline__ int full_pixel_search_pass(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv,
+                                                   unsigned char *winbuf) {
   int run_mesh = 1;
-  int var = full_pixel_diamond<T, W, SKIP>(S, start, P.step_param, best_mv, sw);
+  int var = full_pixel_diamond<T, W, SKIP>(S, start, P.step_param, best_mv);
   int prune = 0, thr = 4;
   if (P.prune_level == 2) prune = 1;
   if (P.prune_level == 1) {
@@ -442,14 +574,13 @@ __device__ int full_pixel_search_pass(const Search<T> &S, const KParams &P, MV2 
     if (d <= thr) run_mesh = 0;
   }
   if (SKIP) {
-    // sdf and sdsf at best_mv: the lane layout of this pass is the skip one, so
-    // use the column-wise generic SAD here (two evaluations per search).
+    // sdf and sdsf at best_mv, column-wise (two evaluations per search)
     const int lane = lane_id();
     constexpr int RP = 32 / W;
     const int col = lane % W, r0 = lane / W;
     const T *a = S.src, *b = S.ref + best_mv->row * S.stride + best_mv->col;
     unsigned s_all = 0, s_even = 0;
-#pragma unroll 8
+#pragma unroll 4
     for (int i = r0; i < W; i += RP) {
       const unsigned d = (unsigned)iabs((int)__ldg(a + i * S.stride + col) - (int)__ldg(b + i * S.stride + col));
       s_all += d;
@@ -464,7 +595,7 @@ __device__ int full_pixel_search_pass(const Search<T> &S, const KParams &P, MV2 
   }
   if (run_mesh) {
     MV2 tmp;
-    const int var_ex = full_pixel_exhaustive<T, W, SKIP>(S, P, *best_mv, &tmp, sw);
+    const int var_ex = full_pixel_exhaustive<T, W, SKIP>(S, P, *best_mv, &tmp, winbuf);
     if (var_ex < var) {
       var = var_ex;
       *best_mv = tmp;
@@ -474,11 +605,19 @@ __device__ int full_pixel_search_pass(const Search<T> &S, const KParams &P, MV2 
 }
 
 template <typename T, int W>
-__device__ void full_pixel_search(const Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv) {
+__device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv, unsigned char *winbuf) {
+  const int wr = iclamp(start.row, S.lim.row_min, S.lim.row_max);
+  const int wc = iclamp(start.col, S.lim.col_min, S.lim.col_max);
+  window_load<T, W>(S, winbuf, wr, wc);
   if (P.use_skip) {
-    if (!full_pixel_search_pass<T, W, true>(S, P, start, best_mv)) return;
+    if (!full_pixel_search_pass<T, W, true>(S, P, start, best_mv, winbuf)) {
+      S.win = nullptr;
+      return;
+    }
+    if (S.wr != wr || S.wc != wc) window_load<T, W>(S, winbuf, wr, wc);
   }
-  full_pixel_search_pass<T, W, false>(S, P, start, best_mv);
+  full_pixel_search_pass<T, W, false>(S, P, start, best_mv, winbuf);
+  S.win = nullptr;
 }
 
 // ---------------------------------------------------------------------------
@@ -487,7 +626,7 @@ __device__ void full_pixel_search(const Search<T> &S, const KParams &P, MV2 star
 // aom_sub_pixel_variance (aom_dsp/variance.c:91-139,150-163; hbd :478-560):
 // 2-tap bilinear over (W+1) x (W+1) samples then variance(filtered, src).
 template <typename T, int W>
-__device__ unsigned bilinear_err(const Search<T> &S, int r8, int c8) {
+__device__ __noinline__ unsigned bilinear_err(const Search<T> &S, int r8, int c8) {
   const int lane = lane_id();
   const T *ref = S.ref + (r8 >> 3) * S.stride + (c8 >> 3);
   const int xo = c8 & 7, yo = r8 & 7;
@@ -529,7 +668,7 @@ __device__ __forceinline__ int clip_px(int v, int bd) {
 // :36-72; pixel-range intermediate), then vf(pred, src) (mcomp.c:2385,2405).
 // tmp: warp-private shared scratch of at least (W+7)*W samples of T.
 template <typename T, int W>
-__device__ unsigned upsampled_err(const Search<T> &S, int r8, int c8, int bd, T *tmp) {
+__device__ __noinline__ unsigned upsampled_err(const Search<T> &S, int r8, int c8, int bd, T *tmp) {
   const int lane = lane_id();
   const int st = S.stride;
   const T *ref = S.ref + (r8 >> 3) * st + (c8 >> 3);
@@ -655,7 +794,7 @@ __device__ void second_level_v2(Subpel<T, W> &sp, MV2 t, MV2 diag) {
 // av1_find_best_sub_pixel_tree{,_pruned,_pruned_more} (mcomp.c:2844-3133) with
 // cost_list == NULL, forced_stop = EIGHTH_PEL, MV_COST_NONE, unscaled refs.
 template <typename T, int W>
-__device__ unsigned subpel_search(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+__device__ __noinline__ unsigned subpel_search(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
   Subpel<T, W> sp;
   sp.S = &S;
   sp.bd = P.is_hbd ? P.bit_depth : 8;
@@ -699,7 +838,7 @@ __device__ __forceinline__ int rawpel(int x) { return (x + 3 + (x >= 0)) >> 3; }
 // tf_motion_search (temporal_filter.c:87-253)
 template <typename T>
 __device__ void motion_search(const KParams &P, const T *cur, const T *ref, int mb_row, int mb_col, MV2 *ref_mv,
-                              MV2 *sub_mvs, int *sub_mses, T *tmp) {
+                              MV2 *sub_mvs, int *sub_mses, T *tmp, unsigned char *winbuf) {
   const int st = P.pitch[0];
   const int y_offset = mb_row * 32 * st + mb_col * 32;
   Search<T> S;
@@ -708,6 +847,8 @@ __device__ void motion_search(const KParams &P, const T *cur, const T *ref, int 
   S.sse_lambda = P.sse_lambda;
   S.hbd_shift = P.hbd_shift;
   S.is_hbd = P.is_hbd;
+  S.win = nullptr;
+  S.wr = S.wc = S.wR = S.wpitch = S.wshift = 0;
   {  // av1_set_mv_{row,col}_limits (mcomp.h:216-240) + av1_set_mv_search_range (mcomp.c:196-215)
     const int border = P.border, mi_row = mb_row * 8, mi_col = mb_col * 8;
     S.lim.row_min = imax(-(mi_row * 4 + border - 8), -(((mi_row + 8) * 4) + 8));
@@ -723,7 +864,7 @@ __device__ void motion_search(const KParams &P, const T *cur, const T *ref, int 
   S.src = cur + y_offset;
   S.ref = ref + y_offset;
   MV2 best_full;
-  full_pixel_search<T, 32>(S, P, start, &best_full);
+  full_pixel_search<T, 32>(S, P, start, &best_full, winbuf);
   int block_mse;
   MV2 block_mv;
   if (P.force_integer_mv == 1) {
@@ -745,7 +886,7 @@ __device__ void motion_search(const KParams &P, const T *cur, const T *ref, int 
       for (int j = 0; j < 32; j += 16) {
         S.src = cur + y_offset + i * st + j;
         S.ref = ref + y_offset + i * st + j;
-        full_pixel_search<T, 16>(S, P, start, &best_full);
+        full_pixel_search<T, 16>(S, P, start, &best_full, winbuf);
         err = subpel_search<T, 16>(S, P, best_full, &best, tmp);
         sub_mses[idx] = (int)((err + 128u) / 256u);
         sub_mvs[idx] = best;
@@ -780,7 +921,7 @@ __device__ void motion_search(const KParams &P, const T *cur, const T *ref, int 
 // (convolve.c:495-515) with the 12-tap MULTITAP_SHARP2 kernels.
 // ---------------------------------------------------------------------------
 template <typename T>
-__device__ void convolve12(const KParams &P, const T *src, int ss, T *dst, int ds, int w, int h, int sx, int sy,
+__device__ __noinline__ void convolve12(const KParams &P, const T *src, int ss, T *dst, int ds, int w, int h, int sx, int sy,
                            int16_t *im) {
   const int lane = lane_id();
   const int pbd = P.is_hbd ? P.bit_depth : 8;
@@ -958,23 +1099,30 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
 // ---------------------------------------------------------------------------
 // Warp-private shared memory, carved at run time (num_pels = 1024 luma + chroma:
 // 1536 for 4:2:0, 2048 for 4:2:2, 3072 for 4:4:4):
-//   accum u32[num_pels] | sq u32[1024] | lsum u32[1024] | count u16[num_pels] |
-//   pred T-view of u16[num_pels] | im i16[27*16]
+//   accum u32[num_pels] | count u16[num_pels] | union region U
+//   U = sq u32[1024] | lsum u32[1024] | pred (T view of u16[num_pels]) | im i16[27*16]
+// During the full-pel search U holds the reference search window (WIN_BYTES).
 struct WarpSmem {
   uint32_t *accum, *sq, *lsum;
   uint16_t *count, *pred;
   int16_t *im;
+  unsigned char *win;
 };
+__host__ __device__ inline size_t warp_union_bytes(int num_pels) {
+  const size_t u = 2 * 1024 * 4 + (size_t)num_pels * 2 + (16 + 11) * 16 * 2;
+  return u > (size_t)WIN_BYTES ? u : (size_t)WIN_BYTES;
+}
 __host__ __device__ inline size_t warp_smem_bytes(int num_pels) {
-  return (size_t)num_pels * 8 + 2 * 1024 * 4 + (16 + 11) * 16 * 2;
+  return (size_t)num_pels * 6 + warp_union_bytes(num_pels);
 }
 __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels) {
   WarpSmem sm;
   sm.accum = reinterpret_cast<uint32_t *>(raw);
-  sm.sq = sm.accum + num_pels;
+  sm.count = reinterpret_cast<uint16_t *>(sm.accum + num_pels);
+  sm.win = reinterpret_cast<unsigned char *>(sm.count + num_pels);
+  sm.sq = reinterpret_cast<uint32_t *>(sm.win);
   sm.lsum = sm.sq + 1024;
-  sm.count = reinterpret_cast<uint16_t *>(sm.lsum + 1024);
-  sm.pred = sm.count + num_pels;
+  sm.pred = reinterpret_cast<uint16_t *>(sm.lsum + 1024);
   sm.im = reinterpret_cast<int16_t *>(sm.pred + num_pels);
   return sm;
 }
@@ -1024,7 +1172,7 @@ __global__ void __launch_bounds__(32) tf_block_kernel(const __grid_constant__ KP
     for (int pl = 0; pl < 3; pl++) ref[pl] = reinterpret_cast<const T *>(P.frm[frame][pl]);
     MV2 sub_mvs[4] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
     int sub_mses[4] = { INT_MAX_, INT_MAX_, INT_MAX_, INT_MAX_ };
-    motion_search<T>(P, cur[0], ref[0], mb_row, mb_col, &ref_mv, sub_mvs, sub_mses, tmp8);
+    motion_search<T>(P, cur[0], ref[0], mb_row, mb_col, &ref_mv, sub_mvs, sub_mses, tmp8, sm.win);
     build_predictor<T>(P, ref, mb_row, mb_col, sub_mvs, pred, sm.im);
     const size_t bf = (size_t)blk * P.num_frames + frame;
     if (P.d_mvs && lane < 4) {
