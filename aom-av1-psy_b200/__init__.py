@@ -28,7 +28,7 @@ EXPORTS = [
     "tf_gpu_filter", "tf_gpu_filter_dump", "tf_gpu_submit", "tf_gpu_wait", "tf_gpu_cache_frame",
     "tf_gpu_evict_frame", "tf_gpu_filter_resident", "tf_gpu_download_output", "tf_gpu_output_device_plane",
     "tf_gpu_host_register", "tf_gpu_host_unregister", "tf_gpu_last_stats", "tf_gpu_event_record",
-    "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench",
+    "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench", "tf_gpu_last_kernel_times",
 ]
 
 
@@ -106,6 +106,7 @@ def load_library():
     lib.tf_gpu_event_elapsed_ms.argtypes = [vp, i, i, C.POINTER(C.c_float)]
     lib.tf_gpu_synchronize.argtypes = [vp]
     lib.tf_gpu_microbench.argtypes = [vp, i, C.POINTER(C.c_double)]
+    lib.tf_gpu_last_kernel_times.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -317,6 +318,11 @@ class TemporalFilterGpu:
         v = C.c_double()
         self._check(self.lib.tf_gpu_microbench(self.h, kind, C.byref(v)))
         return v.value
+
+    def last_kernel_times(self):
+        ms = (C.c_float * 3)()
+        self._check(self.lib.tf_gpu_last_kernel_times(self.h, ms))
+        return [ms[0], ms[1], ms[2]]
 
     def last_stats(self):
         n, ms = C.c_int(), C.c_float()

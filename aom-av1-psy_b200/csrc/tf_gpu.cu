@@ -59,6 +59,9 @@ struct tf_gpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evk[2] = { nullptr, nullptr };  // after search32, after search16
+  float last_kernel_split[3] = { 0.f, 0.f, 0.f };
+  bool split_valid = false;
   cudaEvent_t user_ev[4] = { nullptr, nullptr, nullptr, nullptr };
   std::vector<DevFrame> cache;
   DevFrame out;
@@ -72,8 +75,8 @@ struct tf_gpu_ctx {
   int last_launches = 0;
   float last_kernel_ms = 0.f;
   // dump buffers (device), grown on demand
-  void *d_dump[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
-  size_t d_dump_sz[5] = { 0, 0, 0, 0, 0 };
+  void *d_dump[9] = {};
+  size_t d_dump_sz[9] = {};
   char err[512] = { 0 };
 };
 
@@ -370,16 +373,48 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     if (dump->accum) { rc = ensure_dump(ctx, 3, (size_t)nblocks_all * K.num_pels * sizeof(uint32_t)); if (rc) return rc; K.d_accum = (uint32_t *)ctx->d_dump[3]; }
     if (dump->count) { rc = ensure_dump(ctx, 4, (size_t)nblocks_all * K.num_pels * sizeof(uint16_t)); if (rc) return rc; K.d_count = (uint16_t *)ctx->d_dump[4]; }
   }
+  {  // search results handed from the search kernels to the filter kernel
+    const size_t bf = (size_t)nblocks_all * p->num_frames;
+    int rc = ensure_dump(ctx, 5, bf * 2 * sizeof(int16_t));
+    if (rc) return rc;
+    rc = ensure_dump(ctx, 6, bf * sizeof(int32_t));
+    if (rc) return rc;
+    rc = ensure_dump(ctx, 7, bf * 8 * sizeof(int16_t));
+    if (rc) return rc;
+    rc = ensure_dump(ctx, 8, bf * 4 * sizeof(int32_t));
+    if (rc) return rc;
+    K.s_blk_mv = (int16_t *)ctx->d_dump[5];
+    K.s_blk_mse = (int32_t *)ctx->d_dump[6];
+    K.s_sub_mv = (int16_t *)ctx->d_dump[7];
+    K.s_sub_mse = (int32_t *)ctx->d_dump[8];
+  }
   const int grid = (K.row_end - K.row_begin) * K.mb_cols;
   if (grid <= 0) return fail(ctx, TF_GPU_ERR_INVALID, "empty row range");
-  const size_t smem = warp_smem_bytes(K.num_pels);
+  const size_t smem_search = WIN_BYTES;
+  const size_t smem_filter = filter_smem_bytes(K.num_pels);
+  const int nref = p->num_frames - 1;
   if (timed) CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  if (g.is_hbd)
-    tf_block_kernel<uint16_t><<<grid, 32, smem, ctx->stream>>>(K);
-  else
-    tf_block_kernel<uint8_t><<<grid, 32, smem, ctx->stream>>>(K);
+  if (g.is_hbd) {
+    if (nref > 0) {
+      tf_search32_kernel<uint16_t><<<grid, 32, smem_search, ctx->stream>>>(K);
+      if (timed) cudaEventRecord(ctx->evk[0], ctx->stream);
+      if (!p->force_integer_mv) tf_search16_kernel<uint16_t><<<grid * 4 * nref, 32, smem_search, ctx->stream>>>(K);
+      if (timed) cudaEventRecord(ctx->evk[1], ctx->stream);
+    }
+    tf_filter_kernel<uint16_t><<<grid, 32, smem_filter, ctx->stream>>>(K);
+  } else {
+    if (nref > 0) {
+      tf_search32_kernel<uint8_t><<<grid, 32, smem_search, ctx->stream>>>(K);
+      if (timed) cudaEventRecord(ctx->evk[0], ctx->stream);
+      if (!p->force_integer_mv) tf_search16_kernel<uint8_t><<<grid * 4 * nref, 32, smem_search, ctx->stream>>>(K);
+      if (timed) cudaEventRecord(ctx->evk[1], ctx->stream);
+    }
+    tf_filter_kernel<uint8_t><<<grid, 32, smem_filter, ctx->stream>>>(K);
+  }
   CU(cudaGetLastError());
   if (timed) CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->last_launches += (nref > 0 ? (p->force_integer_mv ? 1 : 2) : 0);
+  ctx->split_valid = timed && nref > 0;
   ctx->last_launches++;
   return TF_GPU_OK;
 }
@@ -501,6 +536,8 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->evk[0]);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->evk[1]);
   for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->user_ev[i]);
   for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->tickets[i].ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_diff, 16 * sizeof(unsigned long long));
@@ -514,8 +551,8 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   }
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_k12, K12, sizeof(K12));
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_k8, K8, sizeof(K8));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tf_block_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(3072));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(tf_block_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem_bytes(3072));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tf_filter_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem_bytes(3072));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tf_filter_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)filter_smem_bytes(3072));
   if (e != cudaSuccess) {
     tf_gpu_destroy(ctx);
     return e == cudaErrorMemoryAllocation ? TF_GPU_ERR_MEM : TF_GPU_ERR_CUDA;
@@ -533,7 +570,7 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
       if (d.base[p]) cudaFree(d.base[p]);
   for (int p = 0; p < 3; p++)
     if (ctx->out.base[p]) cudaFree(ctx->out.base[p]);
-  for (int i = 0; i < 5; i++)
+  for (int i = 0; i < 9; i++)
     if (ctx->d_dump[i]) cudaFree(ctx->d_dump[i]);
   if (ctx->d_diff) cudaFree(ctx->d_diff);
   if (ctx->h_diff) cudaFreeHost(ctx->h_diff);
@@ -543,6 +580,8 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
     if (ctx->tickets[i].ev) cudaEventDestroy(ctx->tickets[i].ev);
   for (int i = 0; i < 4; i++)
     if (ctx->user_ev[i]) cudaEventDestroy(ctx->user_ev[i]);
+  if (ctx->evk[0]) cudaEventDestroy(ctx->evk[0]);
+  if (ctx->evk[1]) cudaEventDestroy(ctx->evk[1]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -720,6 +759,18 @@ int tf_gpu_host_unregister(tf_gpu_ctx *ctx, void *ptr) {
   if (!ctx || !ptr) return TF_GPU_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
   CU(cudaHostUnregister(ptr));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_last_kernel_times(tf_gpu_ctx *ctx, float ms[3]) {
+  if (!ctx || !ms) return TF_GPU_ERR_INVALID;
+  ms[0] = ms[1] = ms[2] = 0.f;
+  if (!ctx->split_valid) return TF_GPU_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(ctx->ev1));
+  CU(cudaEventElapsedTime(&ms[0], ctx->ev0, ctx->evk[0]));
+  CU(cudaEventElapsedTime(&ms[1], ctx->evk[0], ctx->evk[1]));
+  CU(cudaEventElapsedTime(&ms[2], ctx->evk[1], ctx->ev1));
   return TF_GPU_OK;
 }
 

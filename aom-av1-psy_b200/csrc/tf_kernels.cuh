@@ -1,12 +1,18 @@
 // Device code of the B200 temporal filter.  Hand-written CUDA for sm_100a.
 //
-// One warp owns one 32x32 block of the frame to filter and walks the whole
-// window frame by frame (the reference chains ref_mv from frame to frame,
-// av1/encoder/temporal_filter.c:855-871, so the frame loop is sequential per
-// block while the 2,040 / 8,160 blocks of a 1080p / 4K frame are independent).
-// Motion search, predictor, weights, accumulate/count, normalisation and the
-// FRAME_DIFF reduction are fused: pred / accum / count never leave shared
-// memory.  Every data-dependent decision of the reference's search is replayed
+// The per-block loop of av1_tf_do_filtering_row (temporal_filter.c:788-939) is
+// cut along its real data dependencies into three kernels, each small enough
+// for the 32 KB instruction cache (the single fused kernel of the first version
+// stalled 54% of its issue slots on instruction fetch):
+//   tf_search32_kernel  32x32 search of every frame, chained through ref_mv
+//                       (:855-871): one warp per block;
+//   tf_search16_kernel  the 16x16 sub-block searches: one warp per independent
+//                       (frame, block, sub-block) task -- 56x more parallelism
+//                       than blocks for a 15-frame window;
+//   tf_filter_kernel    partition decision, 12-tap predictor, weights,
+//                       accumulate/count, normalise, FRAME_DIFF: pred / accum /
+//                       count never leave shared memory.
+// Every data-dependent decision of the reference's search is replayed
 // warp-uniformly (all lanes take the same branch after a shuffle reduction), so
 // motion vectors are bit-exact by construction.
 //
@@ -63,8 +69,13 @@ struct KParams {
   int16_t *d_mvs;
   int32_t *d_mses;
   uint16_t *d_pred;
-  uint32_t *d_accum;
+  uint32_t *d_accum;  // optional dump of the final accumulators [blocks][num_pels]
   uint16_t *d_count;
+  // search results, [blocks][num_frames] and [blocks][num_frames][4] (device scratch)
+  int16_t *s_blk_mv;   // 32x32 result (row, col) in 1/8 pel
+  int32_t *s_blk_mse;
+  int16_t *s_sub_mv;   // 16x16 results
+  int32_t *s_sub_mse;
   int num_pels;
 };
 
@@ -626,31 +637,43 @@ __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2
 // aom_sub_pixel_variance (aom_dsp/variance.c:91-139,150-163; hbd :478-560):
 // 2-tap bilinear over (W+1) x (W+1) samples then variance(filtered, src).
 template <typename T, int W>
-__device__ __noinline__ unsigned bilinear_err(const Search<T> &S, int r8, int c8) {
+__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8) {
+  const Search<T> S = S_in;
   const int lane = lane_id();
-  const T *ref = S.ref + (r8 >> 3) * S.stride + (c8 >> 3);
+  const int fr = r8 >> 3, fc = c8 >> 3;
   const int xo = c8 & 7, yo = r8 & 7;
   const int f0 = 128 - 16 * xo, f1 = 16 * xo, g0 = 128 - 16 * yo, g1 = 16 * yo;
   constexpr int BANDS = 32 / W;      // 1 (W=32) or 2 (W=16)
   constexpr int BROWS = W / BANDS;   // rows per band
+  constexpr int CH = 8;              // rows per chunk: all loads of a chunk are issued before use
   const int col = lane % W, band = lane / W;
   const int rbeg = band * BROWS;
+  // (fr, fc) and (fr + 1, fc + 1) inside the search window -> read it from shared memory
+  const SadSrc Q = sad_src(S, window_covers(S, fr, fc, 1) && S.wr - fr < S.wR && S.wc - fc < S.wR);
+  const unsigned char *rb = Q.base + (fr + rbeg) * Q.pitchB + (fc + col) * (int)sizeof(T);
+  const T *sp = S.src + rbeg * S.stride + col;
   int sum = 0;
   unsigned sse = 0;
-  int hprev = 0;
-#pragma unroll 3
-  for (int t = 0; t <= BROWS; t++) {
-    const int i = rbeg + t;
-    const T *rp = ref + i * S.stride + col;
-    const int h = rpot((int)__ldg(rp) * f0 + (int)__ldg(rp + 1) * f1, 7);
-    if (t > 0) {
-      int v = rpot(hprev * g0 + h * g1, 7);
+#pragma unroll 1
+  for (int t0 = 0; t0 < BROWS; t0 += CH) {
+    int h[CH + 1], sv[CH];
+#pragma unroll
+    for (int k = 0; k <= CH; k++) {
+      const T *rp = reinterpret_cast<const T *>(rb + (t0 + k) * Q.pitchB);
+      const int a0 = (k < CH || yo) ? (int)rp[0] : 0;
+      const int a1 = (xo && (k < CH || yo)) ? (int)rp[1] : 0;
+      h[k] = xo ? rpot(a0 * f0 + a1 * f1, 7) : a0;
+    }
+#pragma unroll
+    for (int k = 0; k < CH; k++) sv[k] = (int)__ldg(sp + (t0 + k) * S.stride);
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      int v = yo ? rpot(h[k] * g0 + h[k + 1] * g1, 7) : h[k];
       if (sizeof(T) == 1) v &= 0xff;
-      const int d = v - (int)__ldg(S.src + (i - 1) * S.stride + col);
+      const int d = v - sv[k];
       sum += d;
       sse += (unsigned)(d * d);
     }
-    hprev = h;
   }
   sum = warp_sum_i32(sum);
   const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
@@ -835,83 +858,119 @@ __device__ __noinline__ unsigned subpel_search(const Search<T> &S, const KParams
 
 __device__ __forceinline__ int rawpel(int x) { return (x + 3 + (x >= 0)) >> 3; }  // GET_MV_RAWPEL mv.h:28
 
-// tf_motion_search (temporal_filter.c:87-253)
+// tf_motion_search (temporal_filter.c:87-253) is split along its own data
+// dependencies into three kernels (see tf_search32_kernel below):
+//   * the ref_mv chain runs through the 32x32 search only (:182-188,:249-252);
+//   * the four 16x16 searches of a (block, frame) start from the 32x32 result
+//     and are independent of everything else (:190-237);
+//   * the partition decision (:245, :270-292) needs both and happens in the
+//     filter kernel.
 template <typename T>
-__device__ void motion_search(const KParams &P, const T *cur, const T *ref, int mb_row, int mb_col, MV2 *ref_mv,
-                              MV2 *sub_mvs, int *sub_mses, T *tmp, unsigned char *winbuf) {
-  const int st = P.pitch[0];
-  const int y_offset = mb_row * 32 * st + mb_col * 32;
-  Search<T> S;
-  S.stride = st;
+__device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int mb_row, int mb_col) {
+  S.stride = P.pitch[0];
   S.sad_lambda = P.sad_lambda;
   S.sse_lambda = P.sse_lambda;
   S.hbd_shift = P.hbd_shift;
   S.is_hbd = P.is_hbd;
   S.win = nullptr;
   S.wr = S.wc = S.wR = S.wpitch = S.wshift = 0;
-  {  // av1_set_mv_{row,col}_limits (mcomp.h:216-240) + av1_set_mv_search_range (mcomp.c:196-215)
-    const int border = P.border, mi_row = mb_row * 8, mi_col = mb_col * 8;
-    S.lim.row_min = imax(-(mi_row * 4 + border - 8), -(((mi_row + 8) * 4) + 8));
-    S.lim.row_max = imin((P.mi_rows - mi_row - 8) * 4 + border - 8, (P.mi_rows - mi_row) * 4 + 8);
-    S.lim.col_min = imax(-(mi_col * 4 + border - 8), -(((mi_col + 8) * 4) + 8));
-    S.lim.col_max = imin((P.mi_cols - mi_col - 8) * 4 + border - 8, (P.mi_cols - mi_col) * 4 + 8);
-    S.lim.col_min = imax(S.lim.col_min, -1023);
-    S.lim.col_max = imin(S.lim.col_max, 1023);
-    S.lim.row_min = imax(S.lim.row_min, -1023);
-    S.lim.row_max = imin(S.lim.row_max, 1023);
-  }
-  MV2 start = { rawpel(ref_mv->row), rawpel(ref_mv->col) };
+  // av1_set_mv_{row,col}_limits (mcomp.h:216-240) + av1_set_mv_search_range (mcomp.c:196-215)
+  const int border = P.border, mi_row = mb_row * 8, mi_col = mb_col * 8;
+  S.lim.row_min = imax(-(mi_row * 4 + border - 8), -(((mi_row + 8) * 4) + 8));
+  S.lim.row_max = imin((P.mi_rows - mi_row - 8) * 4 + border - 8, (P.mi_rows - mi_row) * 4 + 8);
+  S.lim.col_min = imax(-(mi_col * 4 + border - 8), -(((mi_col + 8) * 4) + 8));
+  S.lim.col_max = imin((P.mi_cols - mi_col - 8) * 4 + border - 8, (P.mi_cols - mi_col) * 4 + 8);
+  S.lim.col_min = imax(S.lim.col_min, -1023);
+  S.lim.col_max = imin(S.lim.col_max, 1023);
+  S.lim.row_min = imax(S.lim.row_min, -1023);
+  S.lim.row_max = imin(S.lim.row_max, 1023);
+}
+
+// Kernel 1: the 32x32 search of every frame of the window, chained through
+// ref_mv (temporal_filter.c:855-871).  One warp per 32x32 block.
+template <typename T>
+__global__ void __launch_bounds__(32) tf_search32_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = lane_id();
+  const int mb_row = P.row_begin + blockIdx.x / P.mb_cols;
+  const int mb_col = blockIdx.x % P.mb_cols;
+  const int blk = mb_row * P.mb_cols + mb_col;
+  const int st = P.pitch[0];
+  const int y_offset = mb_row * 32 * st + mb_col * 32;
+  const T *cur = reinterpret_cast<const T *>(P.frm[P.filter_idx][0]);
+  Search<T> S;
+  search_init(S, P, mb_row, mb_col);
   S.src = cur + y_offset;
-  S.ref = ref + y_offset;
-  MV2 best_full;
-  full_pixel_search<T, 32>(S, P, start, &best_full, winbuf);
-  int block_mse;
-  MV2 block_mv;
-  if (P.force_integer_mv == 1) {
-    unsigned sse;
-    const unsigned err = variance<T, 32>(S.ref + best_full.row * st + best_full.col, st, S.src, st, S.hbd_shift, &sse);
-    block_mse = (int)((err + 512u) / 1024u);
-    block_mv.row = best_full.row * 8;
-    block_mv.col = best_full.col * 8;
-  } else {
-    MV2 best;
-    unsigned err = subpel_search<T, 32>(S, P, best_full, &best, tmp);
-    block_mse = (int)((err + 512u) / 1024u);
-    block_mv = best;
-    *ref_mv = best;
-    start.row = rawpel(ref_mv->row);
-    start.col = rawpel(ref_mv->col);
-    int idx = 0;
-    for (int i = 0; i < 32; i += 16) {
-      for (int j = 0; j < 32; j += 16) {
-        S.src = cur + y_offset + i * st + j;
-        S.ref = ref + y_offset + i * st + j;
-        full_pixel_search<T, 16>(S, P, start, &best_full, winbuf);
-        err = subpel_search<T, 16>(S, P, best_full, &best, tmp);
-        sub_mses[idx] = (int)((err + 128u) / 256u);
-        sub_mvs[idx] = best;
-        ++idx;
-      }
+  MV2 ref_mv = { 0, 0 };
+  for (int frame = 0; frame < P.num_frames; frame++) {
+    if (frame == P.filter_idx) {
+      ref_mv.row = -ref_mv.row;
+      ref_mv.col = -ref_mv.col;
+      continue;
+    }
+    S.ref = reinterpret_cast<const T *>(P.frm[frame][0]) + y_offset;
+    const MV2 start = { rawpel(ref_mv.row), rawpel(ref_mv.col) };
+    MV2 best_full;
+    full_pixel_search<T, 32>(S, P, start, &best_full, smem_raw);
+    int block_mse;
+    MV2 block_mv;
+    if (P.force_integer_mv == 1) {
+      unsigned sse;
+      const unsigned err =
+          variance<T, 32>(S.ref + best_full.row * st + best_full.col, st, S.src, st, S.hbd_shift, &sse);
+      block_mse = (int)((err + 512u) / 1024u);
+      block_mv.row = best_full.row * 8;
+      block_mv.col = best_full.col * 8;
+    } else {
+      const unsigned err = subpel_search<T, 32>(S, P, best_full, &block_mv, reinterpret_cast<T *>(smem_raw));
+      block_mse = (int)((err + 512u) / 1024u);
+      ref_mv = block_mv;
+    }
+    if (lane == 0) {
+      const size_t bf = (size_t)blk * P.num_frames + frame;
+      P.s_blk_mv[bf * 2 + 0] = (int16_t)block_mv.row;
+      P.s_blk_mv[bf * 2 + 1] = (int16_t)block_mv.col;
+      P.s_blk_mse[bf] = block_mse;
+    }
+    if (block_mse > P.mse_thresh) {  // :249-252
+      ref_mv.row = 0;
+      ref_mv.col = 0;
     }
   }
-  // tf_determine_block_partition (:270-292)
-  int mn = INT_MAX_, mx = -INT_MAX_ - 1;
-  long long sum = 0;
-  for (int i = 0; i < 4; i++) {
-    sum += sub_mses[i];
-    mn = imin(mn, sub_mses[i]);
-    mx = imax(mx, sub_mses[i]);
-  }
-  if ((((long long)block_mse * 15 < sum * 4) && mx - mn < 48) ||
-      (((long long)block_mse * 14 < sum * 4) && mx - mn < 24)) {
-    for (int i = 0; i < 4; i++) {
-      sub_mvs[i] = block_mv;
-      sub_mses[i] = block_mse;
-    }
-  }
-  if (block_mse > P.mse_thresh) {
-    ref_mv->row = 0;
-    ref_mv->col = 0;
+}
+
+// Kernel 2: every 16x16 sub-block search is an independent task
+// (frame, block, sub-block); it starts from the full-pel rounding of the
+// 32x32 result (temporal_filter.c:194) and reuses the 32x32 block's MV limits
+// (:202-205).  One warp per task, frame-major task order for L2 locality.
+template <typename T>
+__global__ void __launch_bounds__(32) tf_search16_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = lane_id();
+  const int nblk = (P.row_end - P.row_begin) * P.mb_cols;
+  const int task = blockIdx.x;
+  const int fidx = task / (nblk * 4);
+  const int rem = task - fidx * nblk * 4;
+  const int bl = rem >> 2, sub = rem & 3;
+  const int frame = fidx < P.filter_idx ? fidx : fidx + 1;
+  const int mb_row = P.row_begin + bl / P.mb_cols;
+  const int mb_col = bl % P.mb_cols;
+  const int blk = mb_row * P.mb_cols + mb_col;
+  const int st = P.pitch[0];
+  const int off = mb_row * 32 * st + mb_col * 32 + (sub >> 1) * 16 * st + (sub & 1) * 16;
+  Search<T> S;
+  search_init(S, P, mb_row, mb_col);
+  S.src = reinterpret_cast<const T *>(P.frm[P.filter_idx][0]) + off;
+  S.ref = reinterpret_cast<const T *>(P.frm[frame][0]) + off;
+  const size_t bf = (size_t)blk * P.num_frames + frame;
+  const MV2 start = { rawpel((int)P.s_blk_mv[bf * 2 + 0]), rawpel((int)P.s_blk_mv[bf * 2 + 1]) };
+  MV2 best_full, best;
+  full_pixel_search<T, 16>(S, P, start, &best_full, smem_raw);
+  const unsigned err = subpel_search<T, 16>(S, P, best_full, &best, reinterpret_cast<T *>(smem_raw));
+  if (lane == 0) {
+    P.s_sub_mv[(bf * 4 + sub) * 2 + 0] = (int16_t)best.row;
+    P.s_sub_mv[(bf * 4 + sub) * 2 + 1] = (int16_t)best.col;
+    P.s_sub_mse[bf * 4 + sub] = (int)((err + 128u) / 256u);
   }
 }
 
@@ -1094,50 +1153,43 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
 }
 
 // ---------------------------------------------------------------------------
-// The fused block kernel: av1_tf_do_filtering_row (temporal_filter.c:788-939)
-// for one 32x32 block per warp.
-// ---------------------------------------------------------------------------
+// Kernel 3: per 32x32 block, for every frame of the window: partition decision,
+// predictor, weights, accumulate; then normalise and FRAME_DIFF
+// (av1_tf_do_filtering_row, temporal_filter.c:857-937).  accum / count / pred
+// never leave shared memory.
 // Warp-private shared memory, carved at run time (num_pels = 1024 luma + chroma:
 // 1536 for 4:2:0, 2048 for 4:2:2, 3072 for 4:4:4):
-//   accum u32[num_pels] | count u16[num_pels] | union region U
-//   U = sq u32[1024] | lsum u32[1024] | pred (T view of u16[num_pels]) | im i16[27*16]
-// During the full-pel search U holds the reference search window (WIN_BYTES).
+//   accum u32[num_pels] | sq u32[1024] | lsum u32[1024] | count u16[num_pels] |
+//   pred (T view of u16[num_pels]) | im i16[27*16]
+// ---------------------------------------------------------------------------
 struct WarpSmem {
   uint32_t *accum, *sq, *lsum;
   uint16_t *count, *pred;
   int16_t *im;
-  unsigned char *win;
 };
-__host__ __device__ inline size_t warp_union_bytes(int num_pels) {
-  const size_t u = 2 * 1024 * 4 + (size_t)num_pels * 2 + (16 + 11) * 16 * 2;
-  return u > (size_t)WIN_BYTES ? u : (size_t)WIN_BYTES;
-}
-__host__ __device__ inline size_t warp_smem_bytes(int num_pels) {
-  return (size_t)num_pels * 6 + warp_union_bytes(num_pels);
+__host__ __device__ inline size_t filter_smem_bytes(int num_pels) {
+  return (size_t)num_pels * 8 + 2 * 1024 * 4 + (16 + 11) * 16 * 2;
 }
 __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels) {
   WarpSmem sm;
   sm.accum = reinterpret_cast<uint32_t *>(raw);
-  sm.count = reinterpret_cast<uint16_t *>(sm.accum + num_pels);
-  sm.win = reinterpret_cast<unsigned char *>(sm.count + num_pels);
-  sm.sq = reinterpret_cast<uint32_t *>(sm.win);
+  sm.sq = sm.accum + num_pels;
   sm.lsum = sm.sq + 1024;
-  sm.pred = reinterpret_cast<uint16_t *>(sm.lsum + 1024);
+  sm.count = reinterpret_cast<uint16_t *>(sm.lsum + 1024);
+  sm.pred = sm.count + num_pels;
   sm.im = reinterpret_cast<int16_t *>(sm.pred + num_pels);
   return sm;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32) tf_block_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(32) tf_filter_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const WarpSmem sm = carve_smem(smem_raw, P.num_pels);
   const int lane = lane_id();
-  const int blk_local = blockIdx.x;
-  const int mb_row = P.row_begin + blk_local / P.mb_cols;
-  const int mb_col = blk_local % P.mb_cols;
+  const int mb_row = P.row_begin + blockIdx.x / P.mb_cols;
+  const int mb_col = blockIdx.x % P.mb_cols;
   const int blk = mb_row * P.mb_cols + mb_col;
   T *pred = reinterpret_cast<T *>(sm.pred);
-  T *tmp8 = reinterpret_cast<T *>(sm.sq);  // 8-tap scratch aliases sq (not live during the search)
 
   for (int i = lane; i < P.num_pels; i += 32) {
     sm.accum[i] = 0;
@@ -1148,11 +1200,8 @@ __global__ void __launch_bounds__(32) tf_block_kernel(const __grid_constant__ KP
   const T *cur[3];
   for (int pl = 0; pl < 3; pl++) cur[pl] = reinterpret_cast<const T *>(P.frm[P.filter_idx][pl]);
 
-  MV2 ref_mv = { 0, 0 };
   for (int frame = 0; frame < P.num_frames; frame++) {
     if (frame == P.filter_idx) {
-      ref_mv.row = -ref_mv.row;
-      ref_mv.col = -ref_mv.col;
       // tf_apply_temporal_filter_self (:406-446)
       int off = 0;
       for (int pl = 0; pl < P.num_planes; pl++) {
@@ -1170,16 +1219,52 @@ __global__ void __launch_bounds__(32) tf_block_kernel(const __grid_constant__ KP
     }
     const T *ref[3];
     for (int pl = 0; pl < 3; pl++) ref[pl] = reinterpret_cast<const T *>(P.frm[frame][pl]);
-    MV2 sub_mvs[4] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };
-    int sub_mses[4] = { INT_MAX_, INT_MAX_, INT_MAX_, INT_MAX_ };
-    motion_search<T>(P, cur[0], ref[0], mb_row, mb_col, &ref_mv, sub_mvs, sub_mses, tmp8, sm.win);
-    build_predictor<T>(P, ref, mb_row, mb_col, sub_mvs, pred, sm.im);
     const size_t bf = (size_t)blk * P.num_frames + frame;
-    if (P.d_mvs && lane < 4) {
-      P.d_mvs[(bf * 4 + lane) * 2 + 0] = (int16_t)sub_mvs[lane].row;
-      P.d_mvs[(bf * 4 + lane) * 2 + 1] = (int16_t)sub_mvs[lane].col;
+    MV2 sub_mvs[4];
+    int sub_mses[4];
+    const MV2 block_mv = { (int)P.s_blk_mv[bf * 2 + 0], (int)P.s_blk_mv[bf * 2 + 1] };
+    const int block_mse = P.s_blk_mse[bf];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (P.force_integer_mv == 1) {  // :861-862: the sub-block arrays keep their initial values
+        sub_mvs[i].row = sub_mvs[i].col = 0;
+        sub_mses[i] = INT_MAX_;
+      } else {
+        sub_mvs[i].row = (int)P.s_sub_mv[(bf * 4 + i) * 2 + 0];
+        sub_mvs[i].col = (int)P.s_sub_mv[(bf * 4 + i) * 2 + 1];
+        sub_mses[i] = P.s_sub_mse[bf * 4 + i];
+      }
     }
-    if (P.d_mses && lane < 4) P.d_mses[bf * 4 + lane] = sub_mses[lane];
+    {  // tf_determine_block_partition (:270-292)
+      int mn = INT_MAX_, mx = -INT_MAX_ - 1;
+      long long sum = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        sum += sub_mses[i];
+        mn = imin(mn, sub_mses[i]);
+        mx = imax(mx, sub_mses[i]);
+      }
+      if ((((long long)block_mse * 15 < sum * 4) && mx - mn < 48) ||
+          (((long long)block_mse * 14 < sum * 4) && mx - mn < 24)) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          sub_mvs[i] = block_mv;
+          sub_mses[i] = block_mse;
+        }
+      }
+    }
+    build_predictor<T>(P, ref, mb_row, mb_col, sub_mvs, pred, sm.im);
+    if (P.d_mvs && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        P.d_mvs[(bf * 4 + i) * 2 + 0] = (int16_t)sub_mvs[i].row;
+        P.d_mvs[(bf * 4 + i) * 2 + 1] = (int16_t)sub_mvs[i].col;
+      }
+    }
+    if (P.d_mses && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) P.d_mses[bf * 4 + i] = sub_mses[i];
+    }
     if (P.d_pred)
       for (int i = lane; i < P.num_pels; i += 32) P.d_pred[bf * P.num_pels + i] = (uint16_t)pred[i];
     apply_filter<T>(P, cur, mb_row, mb_col, sub_mvs, sub_mses, pred, sm.accum, sm.count, sm.sq, sm.lsum);

@@ -172,6 +172,10 @@ int tf_gpu_host_unregister(tf_gpu_ctx *ctx, void *ptr);
  * device time (ms) of the block-filter kernel. */
 int tf_gpu_last_stats(const tf_gpu_ctx *ctx, int *kernel_launches, float *filter_kernel_ms);
 
+/* Device time (ms) of the three kernels of the last filter call:
+ * [0] tf_search32_kernel, [1] tf_search16_kernel, [2] tf_filter_kernel. */
+int tf_gpu_last_kernel_times(tf_gpu_ctx *ctx, float ms[3]);
+
 /* Measurement hooks (bench.py): CUDA events recorded on the context's own
  * stream (the stream every kernel of this library is launched on), slots 0..3. */
 int tf_gpu_event_record(tf_gpu_ctx *ctx, int slot);

@@ -25,4 +25,4 @@ for b in bufs:
     ctx.cache_frame(b)
 for k in range(steps):
     ms, diff = ctx.filter_resident(p, [b.frame_id for b in bufs])
-    print("step", k, "kernel ms", ms, "diff", diff.tolist())
+    print("step", k, "kernel ms", ms, "split", ctx.last_kernel_times(), "diff", diff.tolist())
