@@ -169,14 +169,28 @@ __device__ __noinline__ void window_load(Search<T> &S, unsigned char *buf, int w
   constexpr int CPR = C::ROWB / 16;  // chunks per row
   const size_t gpitch = (size_t)S.stride * sizeof(T);
   __syncwarp();
-  for (int q = lane; q < C::ROWS * CPR; q += 32) {
-    const int row = q / CPR, ch = q - row * CPR;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(ga + row * gpitch + ch * 16));
-    uint32_t *d = reinterpret_cast<uint32_t *>(buf + row * C::PITCH + ch * 16);
-    d[0] = v.x;
-    d[1] = v.y;
-    d[2] = v.z;
-    d[3] = v.w;
+  constexpr int TOTAL = C::ROWS * CPR;
+#pragma unroll 1
+  for (int q0 = 0; q0 < TOTAL; q0 += 32 * 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {  // four independent 16-byte loads in flight per lane
+      const int q = q0 + u * 32 + lane;
+      const int row = q / CPR, ch = q - row * CPR;
+      if (q < TOTAL) v[u] = __ldg(reinterpret_cast<const uint4 *>(ga + row * gpitch + ch * 16));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int q = q0 + u * 32 + lane;
+      const int row = q / CPR, ch = q - row * CPR;
+      if (q < TOTAL) {
+        uint32_t *d = reinterpret_cast<uint32_t *>(buf + row * C::PITCH + ch * 16);
+        d[0] = v[u].x;
+        d[1] = v[u].y;
+        d[2] = v[u].z;
+        d[3] = v[u].w;
+      }
+    }
   }
   __syncwarp();
   S.win = buf;
@@ -286,11 +300,85 @@ __device__ __forceinline__ unsigned sad_single(const Search<T> &S, int r, int c,
   return sad_post<SKIP>(part, S.hbd_shift);
 }
 
+// Sums four per-lane values over the warp with 6 shuffles instead of 20: after
+// two exchange steps every lane owns one of the four values (index
+// ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)), three butterfly steps finish it.
+__device__ __forceinline__ unsigned reduce4_u32(const unsigned (&a)[4], int lane) {
+  const bool hi16 = lane & 16, hi8 = lane & 8;
+  unsigned x0 = hi16 ? a[2] : a[0], y0 = hi16 ? a[0] : a[2];
+  unsigned x1 = hi16 ? a[3] : a[1], y1 = hi16 ? a[1] : a[3];
+  x0 += __shfl_xor_sync(FULL, y0, 16);
+  x1 += __shfl_xor_sync(FULL, y1, 16);
+  unsigned x = hi8 ? x1 : x0, y = hi8 ? x0 : x1;
+  x += __shfl_xor_sync(FULL, y, 8);
+  x += __shfl_xor_sync(FULL, x, 4);
+  x += __shfl_xor_sync(FULL, x, 2);
+  x += __shfl_xor_sync(FULL, x, 1);
+  return x;
+}
+
 template <int FROM>
 __device__ __forceinline__ unsigned group_min_u32(unsigned v) {  // min across lane groups of FROM lanes
 #pragma unroll
   for (int o = FROM; o < 32; o <<= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
   return v;
+}
+
+// ---------------------------------------------------------------------------
+// "Far" candidates (outside the shared-memory window) are read from global
+// memory.  With one row per lane every load instruction touches 32 different
+// 128-byte lines (32 L1 wavefronts); the row-major layout below puts the NW
+// words of a row on NW adjacent lanes, so an instruction covers 32/NW rows and
+// only 32/NW (+ straddle) lines: 4-6x fewer L1 wavefronts per candidate.
+// One candidate occupies the whole warp; the sum is over all 32 lanes.
+// ---------------------------------------------------------------------------
+template <typename T, int W, bool SKIP>
+struct FarL {
+  static constexpr int NW = W * (int)sizeof(T) / 4;  // words (= lanes) per row
+  static constexpr int RPI = 32 / NW;                // rows per instruction
+  static constexpr int ROWS = SKIP ? W / 2 : W;
+  static constexpr int IT = ROWS / RPI;              // iterations
+  static constexpr int RSTEP = SKIP ? 2 : 1;
+};
+
+template <typename T, int W, bool SKIP>
+__device__ __forceinline__ void far_load_src(const T *src, int stride, int lane, uint32_t (&sf)[FarL<T, W, SKIP>::IT]) {
+  using F = FarL<T, W, SKIP>;
+  const int j = lane % F::NW, rr = lane / F::NW;
+#pragma unroll
+  for (int it = 0; it < F::IT; it++)
+    sf[it] = __ldg(reinterpret_cast<const uint32_t *>(src + (it * F::RPI + rr) * F::RSTEP * stride) + j);
+}
+
+// Partial (per-lane) SAD of the candidate at (r, c) read from global memory.
+template <typename T, int W, bool SKIP>
+__device__ __forceinline__ unsigned far_partial(const T *ref, int stride, int r, int c, int lane,
+                                                const uint32_t (&sf)[FarL<T, W, SKIP>::IT]) {
+  using F = FarL<T, W, SKIP>;
+  const int j = lane % F::NW, rr = lane / F::NW;
+  const T *p = ref + (r + rr * F::RSTEP) * stride + c;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3) + j;
+  const unsigned sh = (unsigned)(a & 3) * 8;
+  const int step_words = F::RPI * F::RSTEP * stride * (int)sizeof(T) / 4;
+  uint32_t w0[F::IT], w1[F::IT];
+#pragma unroll
+  for (int it = 0; it < F::IT; it++) {
+    w0[it] = __ldg(wp + it * step_words);
+    w1[it] = __ldg(wp + it * step_words + 1);
+  }
+  unsigned s = 0;
+#pragma unroll
+  for (int it = 0; it < F::IT; it++) {
+    const unsigned x = __funnelshift_r(w0[it], w1[it], sh);
+    if (sizeof(T) == 1) {
+      s = __vsadu4(x, sf[it]) + s;
+    } else {
+      const unsigned d = __vmaxu2(x, sf[it]) - __vminu2(x, sf[it]);
+      s += (d & 0xffffu) + (d >> 16);
+    }
+  }
+  return s;
 }
 
 // ---------------------------------------------------------------------------
@@ -362,6 +450,8 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
   const unsigned char *safe = reinterpret_cast<const unsigned char *>(S.src);
   uint32_t sw[L::NW];
   sad_load_src<T, W, SKIP>(S.src, S.stride, sw);
+  uint32_t sf[FarL<T, W, SKIP>::IT];
+  far_load_src<T, W, SKIP>(S.src, S.stride, lane, sf);
   start.col = iclamp(start.col, S.lim.col_min, S.lim.col_max);
   start.row = iclamp(start.row, S.lim.row_min, S.lim.row_max);
   const int tot_steps = 15 - search_step;
@@ -377,31 +467,53 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
     // all_in tests only the four axis sites (mcomp.c:1339-1344)
     const bool all_in = (best.row - rad >= S.lim.row_min) && (best.row + rad <= S.lim.row_max) &&
                         (best.col - rad >= S.lim.col_min) && (best.col + rad <= S.lim.col_max);
-    const SadSrc Q = sad_src(S, window_covers(S, best.row, best.col, rad));
     unsigned mykey = 0xffffffffu;
+    if (window_covers(S, best.row, best.col, rad)) {
+      const SadSrc Q = sad_src(S, true);
 #pragma unroll 1
-    for (int p0 = 0; p0 * L::CPP < nsites; p0 += PU) {
-      unsigned part[PU];
-      int cost[PU];
-      bool ok[PU];
+      for (int p0 = 0; p0 * L::CPP < nsites; p0 += PU) {
+        unsigned part[PU];
+        int cost[PU];
+        bool ok[PU];
 #pragma unroll
-      for (int u = 0; u < PU; u++) {  // independent loads + partial SADs
-        const int idx = 1 + (p0 + u) * L::CPP + grp;
-        const bool live = idx <= nsites;
-        const int my_r = best.row + c_sites.r[step][live ? idx : 0];
-        const int my_c = best.col + c_sites.c[step][live ? idx : 0];
-        ok[u] = live && (all_in || in_range(S.lim, my_r, my_c));
-        cost[u] = sad_cost(S, my_r, my_c);
-        part[u] = sad_partial<T, W, SKIP>(Q, safe, my_r, my_c, row, ok[u], sw);
-      }
+        for (int u = 0; u < PU; u++) {  // independent loads + partial SADs
+          const int idx = 1 + (p0 + u) * L::CPP + grp;
+          const bool live = idx <= nsites;
+          const int my_r = best.row + c_sites.r[step][live ? idx : 0];
+          const int my_c = best.col + c_sites.c[step][live ? idx : 0];
+          ok[u] = live && (all_in || in_range(S.lim, my_r, my_c));
+          cost[u] = sad_cost(S, my_r, my_c);
+          part[u] = sad_partial<T, W, SKIP>(Q, safe, my_r, my_c, row, ok[u], sw);
+        }
 #pragma unroll
-      for (int u = 0; u < PU; u++) {
-        const unsigned tot = sad_post<SKIP>(seg_reduce_u32<L::LPC>(part[u]), S.hbd_shift) + (unsigned)cost[u];
-        const unsigned key = (tot << 4) | (unsigned)(1 + (p0 + u) * L::CPP + grp);
-        mykey = min(mykey, ok[u] ? key : 0xffffffffu);
+        for (int u = 0; u < PU; u++) {
+          const unsigned tot = sad_post<SKIP>(seg_reduce_u32<L::LPC>(part[u]), S.hbd_shift) + (unsigned)cost[u];
+          const unsigned key = (tot << 4) | (unsigned)(1 + (p0 + u) * L::CPP + grp);
+          mykey = min(mykey, ok[u] ? key : 0xffffffffu);
+        }
       }
+      mykey = group_min_u32<L::LPC>(mykey);
+    } else {
+      // far stage: one candidate per warp pass, row-major lanes, 4 candidates in flight
+      const int mine = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // candidate this lane owns after reduce4
+#pragma unroll 1
+      for (int idx0 = 1; idx0 <= nsites; idx0 += 4) {
+        unsigned part[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int cr = best.row + c_sites.r[step][idx0 + u], cc = best.col + c_sites.c[step][idx0 + u];
+          const bool ok = all_in || in_range(S.lim, cr, cc);
+          part[u] = ok ? far_partial<T, W, SKIP>(S.ref, S.stride, cr, cc, lane, sf) : 0u;
+        }
+        const unsigned tot4 = reduce4_u32(part, lane);
+        const int my_r = best.row + c_sites.r[step][idx0 + mine], my_c = best.col + c_sites.c[step][idx0 + mine];
+        const unsigned tot = sad_post<SKIP>(tot4, S.hbd_shift) + (unsigned)sad_cost(S, my_r, my_c);
+        const unsigned key = (tot << 4) | (unsigned)(idx0 + mine);
+        mykey = min(mykey, (all_in || in_range(S.lim, my_r, my_c)) ? key : 0xffffffffu);
+      }
+      mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 8));
+      mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 16));
     }
-    mykey = group_min_u32<L::LPC>(mykey);
     int best_site = 0;
     if ((mykey >> 4) < bestsad) {
       bestsad = mykey >> 4;
