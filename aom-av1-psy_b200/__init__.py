@@ -143,19 +143,27 @@ class Yv12Buffer:
         return self.alloc[p][by:, bx:]
 
     def set_planes(self, y, u=None, v=None, extend=True):
-        """Copy crop-sized planes in; with extend, replicate edges into the whole border
-        (what av1_copy_and_extend_frame leaves in a lookahead slot, extend.c:113-163)."""
+        """Copy crop-sized planes in; with extend, replicate edges with the extents of
+        av1_copy_and_extend_frame (extend.c:113-131): top/left = border, right/bottom =
+        max(aligned + border, align64(aligned)) - crop (chroma: luma extents >> ss)."""
+        aw, ah = self.aligned[0]
+        er_y = max(aw + self.border, _align(aw, 64)) - self.width
+        eb_y = max(ah + self.border, _align(ah, 64)) - self.height
         for p, src in enumerate((y, u, v)[: self.num_planes]):
             k = 1 if p else 0
             cw, ch = self.crop[k]
             bx, by = self.borders[k]
+            er = er_y >> self.ss_x if p else er_y
+            eb = eb_y >> self.ss_y if p else eb_y
             a = self.alloc[p]
             a[by:by + ch, bx:bx + cw] = src
             if extend:
+                x1 = min(bx + cw + er, a.shape[1])
+                y1 = min(by + ch + eb, a.shape[0])
                 a[by:by + ch, :bx] = a[by:by + ch, bx:bx + 1]
-                a[by:by + ch, bx + cw:] = a[by:by + ch, bx + cw - 1:bx + cw]
-                a[:by, :] = a[by:by + 1, :]
-                a[by + ch:, :] = a[by + ch - 1:by + ch, :]
+                a[by:by + ch, bx + cw:x1] = a[by:by + ch, bx + cw - 1:bx + cw]
+                a[:by, :x1] = a[by:by + 1, :x1]
+                a[by + ch:y1, :x1] = a[by + ch - 1:by + ch, :x1]
         return self
 
     def c_frame(self):

@@ -1,0 +1,138 @@
+"""GPU: the C ABI beyond the plain filter call -- reference fixtures, device frame cache,
+resident variant, slab (row-range) mode, async submit/wait, error behaviour."""
+import os
+
+import numpy as np
+import pytest
+
+import _clips
+import _gpu
+import _params
+from golden.make_golden import PIPELINE_CASES, make_frames
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_r01.npz"))
+
+
+@pytest.mark.parametrize("case", PIPELINE_CASES, ids=[c[0] for c in PIPELINE_CASES])
+def test_gpu_matches_reference_fixture(pkg, tfgpu, case):
+    """CUDA path vs outputs of the unmodified reference (no oracle in between)."""
+    name, W, H, N, bd, kind, ckw, pkw = case
+    frames = make_frames(kind, W, H, N, bd, ckw, pkw)
+    p = _params.tf_params(W, H, N, bit_depth=bd, **pkw)
+    b = pkg.Yv12Buffer(W, H, p["ss_x"], p["ss_y"], p["use_hbd"], p["border"], p["monochrome"])
+    b.set_planes(*frames[p["filter_frame_idx"]])
+    noise = [tfgpu.estimate_noise_from_single_plane(b, pl, bd) for pl in range(b.num_planes)]
+    assert noise == list(G[f"{name}/noise"][: len(noise)])
+    p["noise_levels"] = tuple(G[f"{name}/noise"])
+    g = _gpu.run_gpu(pkg, tfgpu, p, frames)
+    sel = [f for f in range(N) if f != p["filter_frame_idx"]]
+    assert (g["mvs"][:, sel] == G[f"{name}/mvs"][:, sel]).all()
+    assert (g["mses"][:, sel] == G[f"{name}/mses"][:, sel]).all()
+    w = np.arange(1, g["pred"].shape[2] + 1, dtype=np.uint64)
+    assert (g["pred"].astype(np.uint64).sum(axis=2)[:, sel] == G[f"{name}/pred_sum"][:, sel]).all()
+    assert ((g["pred"].astype(np.uint64) * w).sum(axis=2)[:, sel] == G[f"{name}/pred_wsum"][:, sel]).all()
+    bad = 0
+    for i, out in enumerate(g["out"]):
+        d = np.abs(out.astype(np.int32) - G[f"{name}/out{i}"].astype(np.int32))
+        assert d.max() <= 1  # +-1 LSB bar for the float-weighted output
+        bad += int((d > 0).sum())
+    assert bad == 0, f"{bad} pixels differ by 1 LSB"  # in practice bit-exact
+    assert (g["diff"] == G[f"{name}/diff"]).all()
+
+
+def _bufs(pkg, p, frames, id_base):
+    out = []
+    for i, (y, u, v) in enumerate(frames):
+        b = pkg.Yv12Buffer(p["width"], p["height"], p["ss_x"], p["ss_y"], p["use_hbd"], p["border"],
+                           p["monochrome"], frame_id=id_base + i if id_base else 0)
+        out.append(b.set_planes(y, u, v, extend=False))
+    return out
+
+
+def test_frame_cache_and_resident_call(pkg, tfgpu):
+    W, H, N = 352, 288, 5
+    frames = _clips.moving_texture(W, H, N, 10)
+    p = _params.tf_params(W, H, N, bit_depth=10)
+    ref = _gpu.run_gpu(pkg, tfgpu, p, frames, dump=False)
+    bufs = _bufs(pkg, p, frames, 5000)
+    for b in bufs:
+        tfgpu.cache_frame(b)
+    ms, diff = tfgpu.filter_resident(p, [b.frame_id for b in bufs])
+    assert ms > 0 and (diff == ref["diff"]).all()
+    out = pkg.Yv12Buffer(W, H, 1, 1, True, p["border"])
+    tfgpu.download_output(out)
+    for pl in range(3):
+        assert (out.full_blocks(pl) == ref["out"][pl]).all()
+    # cached ids are reused: overwrite the host copies, the result must not change
+    for b in bufs:
+        for a in b.alloc:
+            a[:] = 0
+    out2 = pkg.Yv12Buffer(W, H, 1, 1, True, p["border"])
+    r2 = tfgpu.temporal_filter(p, bufs, out2)
+    assert (r2["diff"] == ref["diff"]).all()
+    tfgpu.evict_frame(bufs[0].frame_id)
+    with pytest.raises(pkg.TfGpuError):
+        tfgpu.filter_resident(p, [b.frame_id for b in bufs])
+    for b in bufs:
+        tfgpu.evict_frame(b.frame_id)
+
+
+def test_slab_rows_equal_full_frame(pkg, tfgpu):
+    """Slab mode (4K config): disjoint block-row ranges computed separately equal the full run;
+    FRAME_DIFF adds up."""
+    W, H, N = 352, 288, 3
+    frames = _clips.moving_texture(W, H, N, 8)
+    p = _params.tf_params(W, H, N)
+    full = _gpu.run_gpu(pkg, tfgpu, p, frames, dump=False)
+    mb_rows = (H + 31) // 32
+    out = pkg.Yv12Buffer(W, H, 1, 1, False, p["border"])
+    diff = np.zeros(2, np.int64)
+    for b, e in ((0, 4), (4, mb_rows)):
+        q = dict(p, out_row_begin=b, out_row_end=e)
+        r = tfgpu.temporal_filter(q, _bufs(pkg, p, frames, 0), out)
+        diff += r["diff"]
+    for pl in range(3):
+        assert (out.full_blocks(pl) == full["out"][pl]).all()
+    assert (diff == full["diff"]).all()
+
+
+def test_async_submit_wait(pkg, tfgpu):
+    W, H, N = 176, 144, 3
+    frames = _clips.moving_texture(W, H, N, 8)
+    p = _params.tf_params(W, H, N)
+    full = _gpu.run_gpu(pkg, tfgpu, p, frames, dump=False)
+    outs = [pkg.Yv12Buffer(W, H, 1, 1, False, p["border"]) for _ in range(3)]
+    bufs = _bufs(pkg, p, frames, 0)
+    tickets = [tfgpu.submit(p, bufs, o) for o in outs]
+    for (t, diff, _keep), o in zip(tickets, outs):
+        tfgpu.wait(t)
+        assert [diff[0], diff[1]] == list(full["diff"])
+        assert (o.full_blocks(0) == full["out"][0]).all()
+
+
+def test_invalid_arguments_return_errors(pkg, tfgpu):
+    W, H, N = 64, 64, 3
+    frames = _clips.moving_texture(W, H, N, 8)
+    p = _params.tf_params(W, H, N)
+    bufs = _bufs(pkg, p, frames, 0)
+    out = pkg.Yv12Buffer(W, H, 1, 1, False, p["border"])
+    for bad in (dict(num_frames=0), dict(num_frames=99), dict(filter_frame_idx=7), dict(bit_depth=9),
+                dict(subpel_method=5), dict(filter_strength=9)):
+        with pytest.raises(pkg.TfGpuError) as e:
+            tfgpu.temporal_filter(dict(p, **bad), bufs, out)
+        assert e.value.code == -1
+    with pytest.raises(pkg.TfGpuError):  # 8-bit container with bit_depth 10
+        tfgpu.temporal_filter(dict(p, bit_depth=10), bufs, out)
+    # the context stays usable after an error
+    tfgpu.temporal_filter(p, bufs, out)
+
+
+def test_single_frame_window_is_identity(pkg, tfgpu):
+    """arnr_max_frames = 1 disables filtering (temporal_filter.c:995-997): only the self term."""
+    W, H = 96, 64
+    frames = _clips.moving_texture(W, H, 1, 8)
+    p = _params.tf_params(W, H, 1)
+    g = _gpu.run_gpu(pkg, tfgpu, p, frames, dump=False)
+    assert (g["out"][0][:H, :W] == frames[0][0]).all()
+    assert (g["diff"] == 0).all()
