@@ -248,11 +248,12 @@ class TemporalFilterGpu:
         """frames: list of Yv12Buffer; out: Yv12Buffer.  Returns dict(diff=[sum, sse], mvs, mses, pred, accum, count)."""
         cp = make_params(params) if isinstance(params, dict) else params
         n = cp.num_frames
-        arr = (Frame * n)(*[f.c_frame() for f in frames])
+        arr = (Frame * max(len(frames), 1))(*[f.c_frame() for f in frames])
         co = out.c_frame()
         diff = (C.c_int64 * 2)()
         res = {}
         if dump:
+            n = max(n, 1)
             mb_rows, mb_cols = (out.height + 31) // 32, (out.width + 31) // 32
             nb = mb_rows * mb_cols
             num_pels = 1024 + (0 if cp.num_planes == 1 else 2 * (1024 >> (out.ss_x + out.ss_y)))
@@ -270,7 +271,7 @@ class TemporalFilterGpu:
 
     def submit(self, params, frames, out):
         cp = make_params(params) if isinstance(params, dict) else params
-        arr = (Frame * cp.num_frames)(*[f.c_frame() for f in frames])
+        arr = (Frame * max(len(frames), 1))(*[f.c_frame() for f in frames])
         co = out.c_frame()
         diff = (C.c_int64 * 2)()
         t = C.c_uint64()
