@@ -27,6 +27,7 @@
 #include "av1/encoder/encoder.h"
 #include "av1/encoder/encoder_utils.h"
 #include "av1/encoder/extend.h"
+#include "av1/encoder/lookahead.h"
 
 #define TFREF_API __attribute__((visibility("default")))
 
@@ -137,10 +138,13 @@ typedef struct {
   int compute_frame_diff;
 } tfref_cfg;
 
+/* A frame lives inside a lookahead_entry, as in the encoder (lookahead.h:33-39), so the
+ * CONFIG_TF_GPU seam can recover display_idx from the YV12 pointer. */
 typedef struct {
-  YV12_BUFFER_CONFIG buf;
-  uint8_t *alloc;
+  struct lookahead_entry entry;
 } tfref_frame;
+#define buf entry.img
+static int g_display_idx = 0;
 
 static int align_pow2(int v, int n) { return (v + (1 << n) - 1) & ~((1 << n) - 1); }
 
@@ -149,6 +153,7 @@ static int align_pow2(int v, int n) { return (v + (1 << n) - 1) & ~((1 << n) - 1
  * reference's aom_realloc_frame_buffer itself. */
 static int tfref_frame_alloc(tfref_frame *f, const tfref_cfg *c) {
   memset(f, 0, sizeof(*f));
+  f->entry.display_idx = g_display_idx++;
   return aom_realloc_frame_buffer(&f->buf, c->width, c->height, c->ss_x, c->ss_y,
                                   c->use_hbd, c->border, 0, NULL, NULL, NULL, 0,
                                   0);
@@ -186,6 +191,7 @@ static void tfref_frame_fill(tfref_frame *f, const tfref_cfg *c,
     src.v_buffer = (uint8_t *)planes[2];
   }
   f->buf.monochrome = c->monochrome;
+  f->entry.display_idx = g_display_idx++; /* new pixels, new id */
   av1_copy_and_extend_frame(&src, &f->buf);
 }
 
@@ -283,6 +289,9 @@ TFREF_API void *tfref_create(const tfref_cfg *cfg) {
   mv_sf->subpel_iters_per_step = cfg->subpel_iters_per_step;
   mv_sf->use_accurate_subpel_search = USE_8_TAPS;
   mv_sf->use_fullpel_costlist = 0;
+  mv_sf->subpel_search_method = cfg->subpel_method == 0   ? SUBPEL_TREE
+                                : cfg->subpel_method == 1 ? SUBPEL_TREE_PRUNED
+                                                          : SUBPEL_TREE_PRUNED_MORE;
   /* av1/encoder/speed_features.c:2150-2170 */
   cpi->mv_search_params.find_fractional_mv_step =
       cfg->subpel_method == 0   ? av1_find_best_sub_pixel_tree
@@ -349,10 +358,7 @@ TFREF_API int tfref_get_plane_with_border(void *h, int idx, int plane,
 /* Runs the reference filter over block rows [row_begin,row_end).  Optional
  * recorders may be NULL.  out_{y,u,v} receive mb_rows*32 x mb_cols*32 (luma)
  * samples as u16 (full blocks, temporal_filter.c:740-777). */
-TFREF_API void tfref_run(void *h, int row_begin, int row_end, int16_t *mvs,
-                         int32_t *mses, uint16_t *pred, uint32_t *accum,
-                         uint16_t *count, int64_t *diff_sum_sse) {
-  tfref_ctx *t = (tfref_ctx *)h;
+static void tfref_setup_tf_ctx(tfref_ctx *t) {
   AV1_COMP *cpi = t->cpi;
   const tfref_cfg *c = &t->cfg;
   TemporalFilterCtx *tf_ctx = &cpi->tf_ctx;
@@ -369,6 +375,32 @@ TFREF_API void tfref_run(void *h, int row_begin, int row_end, int16_t *mvs,
   tf_ctx->q_factor = c->q_factor;
   av1_setup_scale_factors_for_frame(&tf_ctx->sf, c->width, c->height, c->width,
                                     c->height);
+}
+
+#if CONFIG_TF_GPU
+/* Runs the reference-side CONFIG_TF_GPU seam (integration/tf_gpu_seam.patch): the exact
+ * code a maintainer adds to av1_temporal_filter(), filling tf_gpu_params / tf_gpu_frame
+ * from AV1_COMP and calling libtf_gpu.so. */
+TFREF_API void tfref_run_gpu_seam(void *h, int64_t *diff_sum_sse) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  tfref_setup_tf_ctx(t);
+  FRAME_DIFF fd = { 0, 0 };
+  tf_gpu_do_filtering(t->cpi, t->cfg.compute_frame_diff ? &fd : NULL);
+  if (diff_sum_sse) {
+    diff_sum_sse[0] = fd.sum;
+    diff_sum_sse[1] = fd.sse;
+  }
+}
+#endif
+
+TFREF_API void tfref_run(void *h, int row_begin, int row_end, int16_t *mvs,
+                         int32_t *mses, uint16_t *pred, uint32_t *accum,
+                         uint16_t *count, int64_t *diff_sum_sse) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  AV1_COMP *cpi = t->cpi;
+  const tfref_cfg *c = &t->cfg;
+  TemporalFilterCtx *tf_ctx = &cpi->tf_ctx;
+  tfref_setup_tf_ctx(t);
 
   ThreadData *td = &cpi->td;
   MACROBLOCKD *mbd = &td->mb.e_mbd;

@@ -6,6 +6,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "..", "oracle", "_ref", "libtf_ref.so")
+# same harness built around temporal_filter.c + integration/tf_gpu_seam.patch, linked to libtf_gpu.so
+SEAM_LIB = os.path.join(HERE, "..", "oracle", "_ref", "libtf_ref_seam.so")
 
 
 class RefCfg(C.Structure):
@@ -30,7 +32,31 @@ def available():
     return os.path.exists(LIB)
 
 
+def seam_available():
+    return os.path.exists(SEAM_LIB)
+
+
 _lib = None
+_seam = None
+
+
+def seam_lib():
+    """The reference + CONFIG_TF_GPU seam; needs libtf_gpu.so and a GPU at call time."""
+    global _seam
+    if _seam is None:
+        _seam = _bind(C.CDLL(SEAM_LIB))
+        _seam.tfref_run_gpu_seam.argtypes = [C.c_void_p, C.c_void_p]
+    return _seam
+
+
+def _bind(l):
+    l.tfref_create.restype = C.c_void_p
+    l.tfref_create.argtypes = [C.POINTER(RefCfg)]
+    l.tfref_set_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.tfref_run.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+    l.tfref_get_output.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    l.tfref_destroy.argtypes = [C.c_void_p]
+    return l
 
 
 def lib():
@@ -74,10 +100,11 @@ def make_cfg(p):
 
 
 class RefFilter:
-    def __init__(self, p, frames):
+    def __init__(self, p, frames, seam=False):
         self.p = dict(p)
         self.cfg = make_cfg(p)
-        self.h = lib().tfref_create(C.byref(self.cfg))
+        self.L = seam_lib() if seam else lib()
+        self.h = self.L.tfref_create(C.byref(self.cfg))
         assert self.h
         self.num_planes = 1 if p["monochrome"] else 3
         self.mb_rows = (p["height"] + 31) // 32
@@ -90,7 +117,7 @@ class RefFilter:
             us = None if u is None else np.ascontiguousarray(u.astype(dt))
             vs = None if v is None else np.ascontiguousarray(v.astype(dt))
             self._keep.append((ys, us, vs))
-            lib().tfref_set_frame(self.h, i, _ptr(ys), _ptr(us), _ptr(vs))
+            self.L.tfref_set_frame(self.h, i, _ptr(ys), _ptr(us), _ptr(vs))
 
     def estimate_noise(self, idx=None):
         idx = self.p["filter_frame_idx"] if idx is None else idx
@@ -104,15 +131,24 @@ class RefFilter:
         pred = np.zeros((nb, nf, self.num_pels), np.uint16) if record else None
         diff = np.zeros(2, np.int64)
         r0, r1 = (0, self.mb_rows) if rows is None else rows
-        lib().tfref_run(self.h, r0, r1, _ptr(mvs), _ptr(mses), _ptr(pred), None, None, _ptr(diff))
+        self.L.tfref_run(self.h, r0, r1, _ptr(mvs), _ptr(mses), _ptr(pred), None, None, _ptr(diff))
+        return dict(mvs=mvs, mses=mses, pred=pred, out=self._outputs(), diff=diff)
+
+    def _outputs(self):
         out = []
         for pl in range(self.num_planes):
             w = self.mb_cols * 32 >> (self.p["ss_x"] if pl else 0)
             h = self.mb_rows * 32 >> (self.p["ss_y"] if pl else 0)
             o = np.zeros((h, w), np.uint16)
-            lib().tfref_get_output(self.h, pl, _ptr(o), w, h)
+            self.L.tfref_get_output(self.h, pl, _ptr(o), w, h)
             out.append(o)
-        return dict(mvs=mvs, mses=mses, pred=pred, out=out, diff=diff)
+        return out
+
+    def run_gpu_seam(self):
+        """av1_temporal_filter()'s CONFIG_TF_GPU branch: the reference-side shim calls libtf_gpu.so."""
+        diff = np.zeros(2, np.int64)
+        self.L.tfref_run_gpu_seam(self.h, _ptr(diff))
+        return dict(out=self._outputs(), diff=diff)
 
     def plane_with_border(self, idx, plane):
         ys, uvs, b, aw, ah = (C.c_int() for _ in range(5))
@@ -129,7 +165,7 @@ class RefFilter:
 
     def close(self):
         if self.h:
-            lib().tfref_destroy(self.h)
+            self.L.tfref_destroy(self.h)
             self.h = None
 
     def __del__(self):
