@@ -1490,18 +1490,18 @@ __global__ void __launch_bounds__(256) microbench_kernel(unsigned *out, int iter
     a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u;
     d[i] = (double)a[i] * 1e-9;
   }
-  const unsigned b = seed | 0x01010101u;
+  const unsigned b = seed | 0x01010101u, c = seed * 7u + 3u;
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        if (KIND == 0) a[i] = a[i] + b + (unsigned)it;                       // IADD3
-        else if (KIND == 1) a[i] = a[i] * b + (unsigned)it;                  // IMAD
-        else if (KIND == 2) a[i] = __vsadu4(a[i] ^ (unsigned)it, b) + a[i];   // VABSDIFF4.ACC (+LOP)
-        else if (KIND == 3) a[i] = __vmaxu2(a[i], b + (unsigned)it);          // VIMNMX.U16x2 (+IADD)
-        else if (KIND == 4) a[i] = __dp4a(a[i], b, a[i]);                     // IDP.4A
-        else d[i] = fma(d[i], 1.0000001, 1e-9);                               // DFMA
+      for (int i = 0; i < 8; i++) {  // opaque single instructions: no algebraic simplification
+        if (KIND == 0) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+        else if (KIND == 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));
+        else if (KIND == 2) asm volatile("vabsdiff4.u32.u32.u32.add %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b), "r"(c));
+        else if (KIND == 3) asm volatile("max.u16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+        else if (KIND == 4) asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b), "r"(c));
+        else asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(1.0000001), "d"(1e-9));
       }
     }
   }

@@ -336,11 +336,14 @@ def main():
 
     ids = [[b.frame_id for b in bufs] for _, bufs in windows]
     launches = 0
+    ktimes = [0.0, 0.0, 0.0]
 
     def step(k):
-        nonlocal launches
+        nonlocal launches, ktimes
         ms, diff = ctx.filter_resident(p, ids[k % nwin])
         launches += ctx.last_stats()[0]
+        for i, t in enumerate(ctx.last_kernel_times()):
+            ktimes[i] += t
         if slab:
             slab_gather(diff)
         return ms
@@ -351,6 +354,7 @@ def main():
     barrier()
     sampler.start()
     launches = 0
+    ktimes = [0.0, 0.0, 0.0]
     ctx.event_record(0)
     t0 = time.perf_counter()
     kernel_ms = 0.0
@@ -403,19 +407,36 @@ def main():
     else:
         hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     rows_frac = ((p["out_row_end"] - p["out_row_begin"]) / mb_rows) if slab else 1.0
-    alg_bytes = (n + 1) * plane_bytes(width, height, bd) * rows_frac
+    es = 2 if use_hbd else 1
+    names = ["tf_search32_kernel", "tf_search16_kernel", "tf_filter_kernel"]
+    kt = [t / args.steps for t in ktimes]  # ms per launch, averaged over the timed steps
+    # algorithmic bytes per launch: every input the kernel must read once + every output written once
+    luma = width * height * es
+    alg = [n * luma * rows_frac + 0.0,                      # search32: luma of all N frames
+           n * luma * rows_frac + 0.0,                      # search16: the same planes again
+           (n + 1) * plane_bytes(width, height, bd) * rows_frac]  # filter: all planes of N frames + the output
+    dom = int(np.argmax(kt))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(wl, {}).get(names[dom])
     kern_s = kern_ms_max * 1e-3 / args.steps
-    achieved = alg_bytes / kern_s / 1e9
-    rates = {k: ctx.microbench(i) for i, k in enumerate(["iadd3", "imad", "vabsdiff4", "vimnmx_u16x2", "idp4a", "dfma"])}
+    achieved = alg[dom] / (kt[dom] * 1e-3) / 1e9
+    rates = {k: ctx.microbench(i) for i, k in enumerate(["iadd", "imad", "vabsdiff4", "vimnmx_u16x2", "idp4a", "dfma"])}
     W = int_work_per_block_ref(p["allow_hp"])
-    r_sad = rates["vabsdiff4"] * 4 if bd == 8 else rates["vimnmx_u16x2"] * 2 / 2  # px per lane-instruction
-    t_int_block = (W["sad"] / r_sad + (W["var"] + W["subpel"] + W["pred"]) / rates["imad"] + W["weights"] / rates["iadd3"]) / 1e9
+    # px per lane-instruction: 8-bit SAD = 4 px per VABSDIFF4.ACC; high bitdepth = 2 px per (max, min, sub-add)
+    r_sad = rates["vabsdiff4"] * 4 if bd == 8 else rates["vimnmx_u16x2"] * 2 / 3
+    t_int_block = (W["sad"] / r_sad + (W["var"] + W["subpel"] + W["pred"]) / rates["imad"] + W["weights"] / rates["iadd"]) / 1e9
     t_int = t_int_block * mb_rows * mb_cols * (n - 1) * rows_frac
+    step_alg = (n + 1) * plane_bytes(width, height, bd) * rows_frac
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "traffic": None, "peak_source": peak_src, "kernel": "tf_block_kernel", "kernel_ms": kern_s * 1e3,
-        "algorithmic_bytes_per_launch": alg_bytes,
-        "int": {"note": "binding roofline per SURVEY 8d: T_int = sum_class W_class / R_class over measured pipe rates",
+        "traffic": traffic, "peak_source": peak_src, "kernel": names[dom], "kernel_ms": kt[dom],
+        "algorithmic_bytes_per_launch": alg[dom],
+        "kernels_ms": dict(zip(names, kt)),
+        "step": {"algorithmic_bytes": step_alg, "kernels_ms_sum": kern_s * 1e3,
+                 "achieved_gbs": step_alg / kern_s / 1e9, "frac": step_alg / kern_s / 1e9 / hbm_peak},
+        "int": {"note": "binding roofline per SURVEY 8d: T_int = sum_class W_class / R_class over measured pipe rates, whole step",
                 "work_per_block_ref": W, "rates_giga_lane_ops_per_s": rates, "t_int_ms": t_int * 1e3,
                 "frac": t_int / kern_s},
     }
