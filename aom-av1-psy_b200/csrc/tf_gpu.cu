@@ -58,6 +58,9 @@ struct Ticket {
 struct tf_gpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // 16x16 searches overlap the 32x32 chain
+  cudaEvent_t ev_f32[TF_GPU_MAX_FRAMES] = {};
+  cudaEvent_t ev_s16 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evk[2] = { nullptr, nullptr };  // after search32, after search16
   float last_kernel_split[3] = { 0.f, 0.f, 0.f };
@@ -75,8 +78,8 @@ struct tf_gpu_ctx {
   int last_launches = 0;
   float last_kernel_ms = 0.f;
   // dump buffers (device), grown on demand
-  void *d_dump[9] = {};
-  size_t d_dump_sz[9] = {};
+  void *d_dump[10] = {};
+  size_t d_dump_sz[10] = {};
   char err[512] = { 0 };
 };
 
@@ -387,6 +390,9 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     K.s_blk_mse = (int32_t *)ctx->d_dump[6];
     K.s_sub_mv = (int16_t *)ctx->d_dump[7];
     K.s_sub_mse = (int32_t *)ctx->d_dump[8];
+    rc = ensure_dump(ctx, 9, (size_t)nblocks_all * 2 * sizeof(int16_t));
+    if (rc) return rc;
+    K.s_ref_mv = (int16_t *)ctx->d_dump[9];
   }
   const int grid = (K.row_end - K.row_begin) * K.mb_cols;
   if (grid <= 0) return fail(ctx, TF_GPU_ERR_INVALID, "empty row range");
@@ -394,26 +400,48 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   const size_t smem_filter = filter_smem_bytes(K.num_pels);
   const int nref = p->num_frames - 1;
   if (timed) CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  if (g.is_hbd) {
-    if (nref > 0) {
-      tf_search32_kernel<uint16_t><<<grid, 32, smem_search, ctx->stream>>>(K);
-      if (timed) cudaEventRecord(ctx->evk[0], ctx->stream);
-      if (!p->force_integer_mv) tf_search16_kernel<uint16_t><<<grid * 4 * nref, 32, smem_search, ctx->stream>>>(K);
-      if (timed) cudaEventRecord(ctx->evk[1], ctx->stream);
+  // Search phase: one search32 launch per reference frame on the main stream (the ref_mv
+  // chain), the independent 16x16 searches of that frame on a second stream as soon as its
+  // 32x32 results exist -> the throughput-bound 16x16 work fills the latency-bound chain.
+  int nlaunch = 0;
+  if (nref > 0) {
+    bool any16 = false;
+    for (int f = 0; f < p->num_frames; f++) {
+      if (f == p->filter_frame_idx) continue;
+      KParams Kf = K;
+      Kf.frame_begin = f;
+      Kf.frame_end = f + 1;
+      if (f > 0 && f - 1 == p->filter_frame_idx) Kf.frame_begin = f - 1;  // negate ref_mv at the centre frame
+      if (g.is_hbd) tf_search32_kernel<uint16_t><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+      else tf_search32_kernel<uint8_t><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+      nlaunch++;
+      if (!p->force_integer_mv) {
+        CU(cudaEventRecord(ctx->ev_f32[f], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_f32[f], 0));
+        Kf.frame_begin = f;
+        Kf.frame_end = f + 1;
+        KParams K16 = Kf;
+        // task decode expects [frame_begin, frame_end) minus the centre: a single non-centre frame
+        K16.filter_idx = K.filter_idx;
+        if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4, 32, smem_search, ctx->stream2>>>(K16);
+        else tf_search16_kernel<uint8_t><<<grid * 4, 32, smem_search, ctx->stream2>>>(K16);
+        nlaunch++;
+        any16 = true;
+      }
     }
-    tf_filter_kernel<uint16_t><<<grid, 32, smem_filter, ctx->stream>>>(K);
-  } else {
-    if (nref > 0) {
-      tf_search32_kernel<uint8_t><<<grid, 32, smem_search, ctx->stream>>>(K);
-      if (timed) cudaEventRecord(ctx->evk[0], ctx->stream);
-      if (!p->force_integer_mv) tf_search16_kernel<uint8_t><<<grid * 4 * nref, 32, smem_search, ctx->stream>>>(K);
-      if (timed) cudaEventRecord(ctx->evk[1], ctx->stream);
+    if (timed) cudaEventRecord(ctx->evk[0], ctx->stream);
+    if (any16) {
+      CU(cudaEventRecord(ctx->ev_s16, ctx->stream2));
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_s16, 0));
     }
-    tf_filter_kernel<uint8_t><<<grid, 32, smem_filter, ctx->stream>>>(K);
+    if (timed) cudaEventRecord(ctx->evk[1], ctx->stream);
   }
+  if (g.is_hbd) tf_filter_kernel<uint16_t><<<grid, 32, smem_filter, ctx->stream>>>(K);
+  else tf_filter_kernel<uint8_t><<<grid, 32, smem_filter, ctx->stream>>>(K);
+  nlaunch++;
   CU(cudaGetLastError());
   if (timed) CU(cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->last_launches += (nref > 0 ? (p->force_integer_mv ? 1 : 2) : 0);
+  ctx->last_launches += nlaunch - 1;
   ctx->split_valid = timed && nref > 0;
   ctx->last_launches++;
   return TF_GPU_OK;
@@ -534,6 +562,9 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   ctx->cache.resize(slots);
   cudaError_t e = cudaSetDevice(dev);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  for (int i = 0; i < TF_GPU_MAX_FRAMES && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_f32[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_s16, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->evk[0]);
@@ -570,7 +601,7 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
       if (d.base[p]) cudaFree(d.base[p]);
   for (int p = 0; p < 3; p++)
     if (ctx->out.base[p]) cudaFree(ctx->out.base[p]);
-  for (int i = 0; i < 9; i++)
+  for (int i = 0; i < 10; i++)
     if (ctx->d_dump[i]) cudaFree(ctx->d_dump[i]);
   if (ctx->d_diff) cudaFree(ctx->d_diff);
   if (ctx->h_diff) cudaFreeHost(ctx->h_diff);
@@ -584,6 +615,13 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
   if (ctx->evk[1]) cudaEventDestroy(ctx->evk[1]);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < TF_GPU_MAX_FRAMES; i++)
+    if (ctx->ev_f32[i]) cudaEventDestroy(ctx->ev_f32[i]);
+  if (ctx->ev_s16) cudaEventDestroy(ctx->ev_s16);
+  if (ctx->stream2) {
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamDestroy(ctx->stream2);
+  }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

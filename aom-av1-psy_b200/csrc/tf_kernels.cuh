@@ -72,6 +72,8 @@ struct KParams {
   uint32_t *d_accum;  // optional dump of the final accumulators [blocks][num_pels]
   uint16_t *d_count;
   // search results, [blocks][num_frames] and [blocks][num_frames][4] (device scratch)
+  int16_t *s_ref_mv;   // [blocks][2]: the ref_mv chain state between per-frame search32 launches
+  int frame_begin, frame_end;  // frames [begin, end) handled by this search launch
   int16_t *s_blk_mv;   // 32x32 result (row, col) in 1/8 pel
   int32_t *s_blk_mse;
   int16_t *s_sub_mv;   // 16x16 results
@@ -1013,8 +1015,13 @@ __global__ void __launch_bounds__(32) tf_search32_kernel(const __grid_constant__
   Search<T> S;
   search_init(S, P, mb_row, mb_col);
   S.src = cur + y_offset;
+  // ref_mv chain (temporal_filter.c:855-871): carried in global memory across launches
   MV2 ref_mv = { 0, 0 };
-  for (int frame = 0; frame < P.num_frames; frame++) {
+  if (P.frame_begin > 0) {
+    ref_mv.row = P.s_ref_mv[blk * 2 + 0];
+    ref_mv.col = P.s_ref_mv[blk * 2 + 1];
+  }
+  for (int frame = P.frame_begin; frame < P.frame_end; frame++) {
     if (frame == P.filter_idx) {
       ref_mv.row = -ref_mv.row;
       ref_mv.col = -ref_mv.col;
@@ -1049,6 +1056,10 @@ __global__ void __launch_bounds__(32) tf_search32_kernel(const __grid_constant__
       ref_mv.col = 0;
     }
   }
+  if (lane == 0) {
+    P.s_ref_mv[blk * 2 + 0] = (int16_t)ref_mv.row;
+    P.s_ref_mv[blk * 2 + 1] = (int16_t)ref_mv.col;
+  }
 }
 
 // Kernel 2: every 16x16 sub-block search is an independent task
@@ -1064,7 +1075,9 @@ __global__ void __launch_bounds__(32) tf_search16_kernel(const __grid_constant__
   const int fidx = task / (nblk * 4);
   const int rem = task - fidx * nblk * 4;
   const int bl = rem >> 2, sub = rem & 3;
-  const int frame = fidx < P.filter_idx ? fidx : fidx + 1;
+  // frames [frame_begin, frame_end) minus the centre frame, in order
+  int frame = P.frame_begin + fidx;
+  if (P.filter_idx >= P.frame_begin && frame >= P.filter_idx) frame++;
   const int mb_row = P.row_begin + bl / P.mb_cols;
   const int mb_col = bl % P.mb_cols;
   const int blk = mb_row * P.mb_cols + mb_col;
