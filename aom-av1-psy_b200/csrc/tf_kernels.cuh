@@ -483,8 +483,9 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
           const bool live = idx <= nsites;
           const int my_r = best.row + c_sites.r[step][live ? idx : 0];
           const int my_c = best.col + c_sites.c[step][live ? idx : 0];
-          ok[u] = live && (all_in || in_range(S.lim, my_r, my_c));
           cost[u] = sad_cost(S, my_r, my_c);
+          // exact pruning: a site is accepted only if sad + cost < bestsad and sad >= 0
+          ok[u] = live && (all_in || in_range(S.lim, my_r, my_c)) && (unsigned)cost[u] < bestsad;
           part[u] = sad_partial<T, W, SKIP>(Q, safe, my_r, my_c, row, ok[u], sw);
         }
 #pragma unroll
@@ -501,17 +502,22 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
 #pragma unroll 1
       for (int idx0 = 1; idx0 <= nsites; idx0 += 4) {
         unsigned part[4];
+        bool any_ok = false;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int cr = best.row + c_sites.r[step][idx0 + u], cc = best.col + c_sites.c[step][idx0 + u];
-          const bool ok = all_in || in_range(S.lim, cr, cc);
+          // exact pruning: sad + cost < bestsad is impossible once cost >= bestsad
+          const bool ok = (all_in || in_range(S.lim, cr, cc)) && (unsigned)sad_cost(S, cr, cc) < bestsad;
+          any_ok |= ok;
           part[u] = ok ? far_partial<T, W, SKIP>(S.ref, S.stride, cr, cc, lane, sf) : 0u;
         }
+        if (!any_ok) continue;
         const unsigned tot4 = reduce4_u32(part, lane);
         const int my_r = best.row + c_sites.r[step][idx0 + mine], my_c = best.col + c_sites.c[step][idx0 + mine];
-        const unsigned tot = sad_post<SKIP>(tot4, S.hbd_shift) + (unsigned)sad_cost(S, my_r, my_c);
+        const unsigned my_cost = (unsigned)sad_cost(S, my_r, my_c);
+        const unsigned tot = sad_post<SKIP>(tot4, S.hbd_shift) + my_cost;
         const unsigned key = (tot << 4) | (unsigned)(idx0 + mine);
-        mykey = min(mykey, (all_in || in_range(S.lim, my_r, my_c)) ? key : 0xffffffffu);
+        mykey = min(mykey, ((all_in || in_range(S.lim, my_r, my_c)) && my_cost < bestsad) ? key : 0xffffffffu);
       }
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 8));
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 16));
@@ -626,14 +632,14 @@ __device__ __noinline__ int mesh_search(const Search<T> &S_in, MV2 start, int ra
       const int ri = qq / n_cols, ci = qq - ri * n_cols;
       const int my_r = start.row + start_row + ri * step, my_c = start.col + start_col + ci * step;
       cost[u] = sad_cost(S, my_r, my_c);
-      part[u] = sad_partial<T, W, SKIP>(Q, safe, my_r, my_c, row, valid, sw);
+      part[u] = sad_partial<T, W, SKIP>(Q, safe, my_r, my_c, row, valid && (unsigned)cost[u] < best_sad, sw);
     }
 #pragma unroll
     for (int u = 0; u < PU; u++) {
       const int q = q0 + u * L::CPP + grp;
       const unsigned tot = sad_post<SKIP>(seg_reduce_u32<L::LPC>(part[u]), S.hbd_shift) + (unsigned)cost[u];
       const unsigned long long key = ((unsigned long long)tot << 32) | (unsigned)q;
-      mykey = (q < total && key < mykey) ? key : mykey;
+      mykey = (q < total && (unsigned)cost[u] < best_sad && key < mykey) ? key : mykey;
     }
   }
 #pragma unroll
@@ -1117,8 +1123,14 @@ __device__ __noinline__ void convolve12(const KParams &P, const T *src, int ss, 
   }
   const int rp = 32 / w;  // rows per iteration (w is 8 or 16)
   const int col = lane % w, rr = lane / w;
-  if (!sx && !sy) {
-    for (int y = rr; y < h; y += rp) dst[y * ds + col] = __ldg(src + y * ss + col);
+  if (!sx && !sy) {  // aom_convolve_copy; h / rp is 4 or 8: all loads in flight
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (rr + k * rp < h) v[k] = __ldg(src + (rr + k * rp) * ss + col);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (rr + k * rp < h) dst[(rr + k * rp) * ds + col] = v[k];
   } else if (sx && !sy) {
     const int16_t *f = c_k12[sx];
     const int bits = 7 - r0b;
