@@ -423,8 +423,8 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
         KParams K16 = Kf;
         // task decode expects [frame_begin, frame_end) minus the centre: a single non-centre frame
         K16.filter_idx = K.filter_idx;
-        if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4, 32, smem_search, ctx->stream2>>>(K16);
-        else tf_search16_kernel<uint8_t><<<grid * 4, 32, smem_search, ctx->stream2>>>(K16);
+        if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4, 32, WIN16_BYTES, ctx->stream2>>>(K16);
+        else tf_search16_kernel<uint8_t><<<grid * 4, 32, WIN16_BYTES, ctx->stream2>>>(K16);
         nlaunch++;
         any16 = true;
       }

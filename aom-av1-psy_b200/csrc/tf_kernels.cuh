@@ -134,7 +134,8 @@ struct Search {
   int wshift;  // bytes the window origin was aligned down by
 };
 
-constexpr int WIN_BYTES = 12288;  // window capacity per warp (aliases sq | lsum | pred | im)
+constexpr int WIN_BYTES = 12288;  // window capacity per warp, 32x32 search
+constexpr int WIN16_BYTES = 4608;  // 16x16 search (R = 12): lets >= 24 warps share an SM
 
 // SAD lane layout: a candidate occupies LPC lanes (one block row per lane, every
 // other row with skip-row SAD, aom_dsp/sad.c:66-70), so a pass evaluates
@@ -152,11 +153,11 @@ struct SadL {
 // Largest window radius that fits WIN_BYTES for a W x W block of T.
 template <typename T, int W>
 struct WinCfg {
-  static constexpr int R = (W == 32) ? 16 : 24;
+  static constexpr int R = (W == 32) ? 16 : 12;
   static constexpr int ROWS = W + 2 * R;
   static constexpr int ROWB = ((W + 2 * R) * (int)sizeof(T) + 15 + 15) / 16 * 16;  // + align-down slack, 16B chunks
   static constexpr int PITCH = ROWB + 4 + ((((ROWB + 4) / 4) & 1) ? 0 : 4);         // words per row odd
-  static_assert(ROWS * PITCH <= WIN_BYTES, "search window does not fit");
+  static_assert(ROWS * PITCH <= (W == 32 ? WIN_BYTES : WIN16_BYTES), "search window does not fit");
 };
 
 // Cooperative, coalesced window fill: 16-byte global loads, 4-byte shared stores.
@@ -274,7 +275,7 @@ __device__ __forceinline__ unsigned sad_partial(const SadSrc &Q, const unsigned 
 // mvsad_err_cost (mcomp.c:310-331), L1, ref = 0
 template <typename T>
 __device__ __forceinline__ int sad_cost(const Search<T> &S, int r, int c) {
-  return (S.sad_lambda * (iabs(r * 8) + iabs(c * 8))) >> 3;
+  return S.sad_lambda * (iabs(r) + iabs(c));  // == (lambda * (|8r| + |8c|)) >> 3 exactly
 }
 // mv_err_cost (mcomp.c:271-295) on a 1/8-pel mv
 template <typename T>
@@ -373,13 +374,10 @@ __device__ __forceinline__ unsigned far_partial(const T *ref, int stride, int r,
 #pragma unroll
   for (int it = 0; it < F::IT; it++) {
     const unsigned x = __funnelshift_r(w0[it], w1[it], sh);
-    if (sizeof(T) == 1) {
-      s = __vsadu4(x, sf[it]) + s;
-    } else {
-      const unsigned d = __vmaxu2(x, sf[it]) - __vminu2(x, sf[it]);
-      s += (d & 0xffffu) + (d >> 16);
-    }
+    if (sizeof(T) == 1) s = __vsadu4(x, sf[it]) + s;
+    else s += __vmaxu2(x, sf[it]) - __vminu2(x, sf[it]);  // packed u16 lanes: IT <= 16 terms of <= 4095, no carry
   }
+  if (sizeof(T) != 1) s = (s & 0xffffu) + (s >> 16);
   return s;
 }
 
@@ -501,23 +499,27 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
       const int mine = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // candidate this lane owns after reduce4
 #pragma unroll 1
       for (int idx0 = 1; idx0 <= nsites; idx0 += 4) {
-        unsigned part[4];
+        unsigned part[4], cst[4];
+        bool okv[4];
         bool any_ok = false;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int cr = best.row + c_sites.r[step][idx0 + u], cc = best.col + c_sites.c[step][idx0 + u];
+          cst[u] = (unsigned)sad_cost(S, cr, cc);
           // exact pruning: sad + cost < bestsad is impossible once cost >= bestsad
-          const bool ok = (all_in || in_range(S.lim, cr, cc)) && (unsigned)sad_cost(S, cr, cc) < bestsad;
-          any_ok |= ok;
-          part[u] = ok ? far_partial<T, W, SKIP>(S.ref, S.stride, cr, cc, lane, sf) : 0u;
+          okv[u] = (all_in || in_range(S.lim, cr, cc)) && cst[u] < bestsad;
+          any_ok |= okv[u];
+          part[u] = okv[u] ? far_partial<T, W, SKIP>(S.ref, S.stride, cr, cc, lane, sf) : 0u;
         }
         if (!any_ok) continue;
         const unsigned tot4 = reduce4_u32(part, lane);
-        const int my_r = best.row + c_sites.r[step][idx0 + mine], my_c = best.col + c_sites.c[step][idx0 + mine];
-        const unsigned my_cost = (unsigned)sad_cost(S, my_r, my_c);
+        // this lane owns candidate `mine` (0..3): pick its cost / validity from the uniform values
+        const unsigned c01 = (mine & 1) ? cst[1] : cst[0], c23 = (mine & 1) ? cst[3] : cst[2];
+        const bool o01 = (mine & 1) ? okv[1] : okv[0], o23 = (mine & 1) ? okv[3] : okv[2];
+        const unsigned my_cost = (mine & 2) ? c23 : c01;
+        const bool my_ok = (mine & 2) ? o23 : o01;
         const unsigned tot = sad_post<SKIP>(tot4, S.hbd_shift) + my_cost;
-        const unsigned key = (tot << 4) | (unsigned)(idx0 + mine);
-        mykey = min(mykey, ((all_in || in_range(S.lim, my_r, my_c)) && my_cost < bestsad) ? key : 0xffffffffu);
+        mykey = min(mykey, my_ok ? ((tot << 4) | (unsigned)(idx0 + mine)) : 0xffffffffu);
       }
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 8));
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 16));
@@ -1073,7 +1075,7 @@ __global__ void __launch_bounds__(32) tf_search32_kernel(const __grid_constant__
 // 32x32 result (temporal_filter.c:194) and reuses the 32x32 block's MV limits
 // (:202-205).  One warp per task, frame-major task order for L2 locality.
 template <typename T>
-__global__ void __launch_bounds__(32) tf_search16_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(32, 24) tf_search16_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id();
   const int nblk = (P.row_end - P.row_begin) * P.mb_cols;
