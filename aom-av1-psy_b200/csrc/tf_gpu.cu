@@ -43,6 +43,7 @@ struct DevFrame {
   Geometry g;
   void *base[3] = { nullptr, nullptr, nullptr };  // allocation base
   void *p00[3] = { nullptr, nullptr, nullptr };   // pixel (0,0)
+  cudaEvent_t ready = nullptr;                    // upload + border extension finished (copy stream)
 };
 
 struct Ticket {
@@ -59,6 +60,9 @@ struct tf_gpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // 16x16 searches overlap the 32x32 chain
+  cudaStream_t copy_stream = nullptr;  // uploads overlap the search of earlier frames
+  cudaEvent_t done_ev = nullptr;       // end of the last submitted call (main stream)
+  bool done_valid = false;
   cudaEvent_t ev_f32[TF_GPU_MAX_FRAMES] = {};
   cudaEvent_t ev_s16 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -154,22 +158,23 @@ int upload_frame(tf_gpu_ctx *ctx, DevFrame *d, const tf_gpu_frame *f) {
     const int k = p > 0;
     if (!f->plane[p]) return fail(ctx, TF_GPU_ERR_INVALID, "frame plane %d is NULL", p);
     CU(cudaMemcpy2DAsync(d->p00[p], (size_t)g.pitch[k] * es, f->plane[p], (size_t)f->stride[k] * es,
-                         (size_t)g.crop_w[k] * es, g.crop_h[k], cudaMemcpyHostToDevice, ctx->stream));
+                         (size_t)g.crop_w[k] * es, g.crop_h[k], cudaMemcpyHostToDevice, ctx->copy_stream));
     const int ext_w = g.aligned_w[k] + g.bx[k], ext_h = g.aligned_h[k] + g.by[k];
     const long long n = (long long)(g.bx[k] + ext_w) * (g.by[k] + ext_h);
     const int threads = 256;
     const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads);
     if (g.is_hbd)
-      extend_borders_kernel<uint16_t><<<blocks, threads, 0, ctx->stream>>>((uint16_t *)d->p00[p], g.pitch[k],
+      extend_borders_kernel<uint16_t><<<blocks, threads, 0, ctx->copy_stream>>>((uint16_t *)d->p00[p], g.pitch[k],
                                                                           g.crop_w[k], g.crop_h[k], g.bx[k], g.by[k],
                                                                           ext_w, ext_h);
     else
-      extend_borders_kernel<uint8_t><<<blocks, threads, 0, ctx->stream>>>((uint8_t *)d->p00[p], g.pitch[k],
+      extend_borders_kernel<uint8_t><<<blocks, threads, 0, ctx->copy_stream>>>((uint8_t *)d->p00[p], g.pitch[k],
                                                                          g.crop_w[k], g.crop_h[k], g.bx[k], g.by[k],
                                                                          ext_w, ext_h);
     ctx->last_launches++;
   }
   CU(cudaGetLastError());
+  CU(cudaEventRecord(d->ready, ctx->copy_stream));
   d->frame_id = f->frame_id;
   d->valid = true;
   return TF_GPU_OK;
@@ -399,6 +404,8 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   const size_t smem_search = WIN_BYTES;
   const size_t smem_filter = filter_smem_bytes(K.num_pels);
   const int nref = p->num_frames - 1;
+  // the frame to filter is read by every kernel
+  CU(cudaStreamWaitEvent(ctx->stream, frames[p->filter_frame_idx]->ready, 0));
   if (timed) CU(cudaEventRecord(ctx->ev0, ctx->stream));
   // Search phase: one search32 launch per reference frame on the main stream (the ref_mv
   // chain), the independent 16x16 searches of that frame on a second stream as soon as its
@@ -412,6 +419,7 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
       Kf.frame_begin = f;
       Kf.frame_end = f + 1;
       if (f > 0 && f - 1 == p->filter_frame_idx) Kf.frame_begin = f - 1;  // negate ref_mv at the centre frame
+      CU(cudaStreamWaitEvent(ctx->stream, frames[f]->ready, 0));  // uploads of later frames overlap this search
       if (g.is_hbd) tf_search32_kernel<uint16_t><<<grid, 32, smem_search, ctx->stream>>>(Kf);
       else tf_search32_kernel<uint8_t><<<grid, 32, smem_search, ctx->stream>>>(Kf);
       nlaunch++;
@@ -495,13 +503,18 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
   if ((int)ctx->cache.size() < params->num_frames) return fail(ctx, TF_GPU_ERR_MEM, "frame cache smaller than the window");
   ctx->epoch++;
   ctx->last_launches = 0;
+  // cache slots may still be read by the kernels of the previous (asynchronous) call
+  if (ctx->done_valid) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev, 0));
   DevFrame *devf[TF_GPU_MAX_FRAMES];
-  for (int i = 0; i < params->num_frames; i++) {
+  // upload order = consumption order: the frame to filter first, then the chain order
+  for (int k = 0; k < params->num_frames; k++) {
+    const int i = k == 0 ? params->filter_frame_idx : (k <= params->filter_frame_idx ? k - 1 : k);
     if (frames[i].is_hbd != frames[0].is_hbd) return fail(ctx, TF_GPU_ERR_INVALID, "mixed bit depth containers");
     rc = get_frame(ctx, &frames[i], params->num_planes, &devf[i]);
     if (rc) return rc;
-    if (!(devf[i]->g == devf[0]->g)) return fail(ctx, TF_GPU_ERR_INVALID, "frames of one window must share geometry");
   }
+  for (int i = 0; i < params->num_frames; i++)
+    if (!(devf[i]->g == devf[0]->g)) return fail(ctx, TF_GPU_ERR_INVALID, "frames of one window must share geometry");
   const Geometry &g = devf[0]->g;
   if (g.is_hbd == 0 && params->bit_depth != 8) return fail(ctx, TF_GPU_ERR_INVALID, "8-bit container needs bit_depth 8");
   rc = alloc_dev_frame(ctx, &ctx->out, g);
@@ -527,6 +540,8 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
   }
   CU(cudaMemcpyAsync(ctx->h_diff + 2 * slot, d_diff, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(t.ev, ctx->stream));
+  CU(cudaEventRecord(ctx->done_ev, ctx->stream));
+  ctx->done_valid = true;
   t.id = ctx->next_ticket++;
   t.diff_dst = diff_sum_sse;
   t.want_diff = diff_sum_sse != nullptr;
@@ -563,6 +578,10 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   cudaError_t e = cudaSetDevice(dev);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming);
+  for (auto &d : ctx->cache)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ready, cudaEventDisableTiming);
   for (int i = 0; i < TF_GPU_MAX_FRAMES && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_f32[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_s16, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
@@ -596,9 +615,14 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  for (auto &d : ctx->cache)
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  for (auto &d : ctx->cache) {
     for (int p = 0; p < 3; p++)
       if (d.base[p]) cudaFree(d.base[p]);
+    if (d.ready) cudaEventDestroy(d.ready);
+  }
+  if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int p = 0; p < 3; p++)
     if (ctx->out.base[p]) cudaFree(ctx->out.base[p]);
   for (int i = 0; i < 10; i++)
@@ -635,9 +659,10 @@ int tf_gpu_cache_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *frame) {
   ctx->epoch++;
   DevFrame *d;
   const int num_planes = frame->plane[1] ? 3 : 1;
+  if (ctx->done_valid) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev, 0));
   int rc = get_frame(ctx, frame, num_planes, &d);
   if (rc) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
   return TF_GPU_OK;
 }
 
@@ -658,8 +683,10 @@ int tf_gpu_estimate_noise(tf_gpu_ctx *ctx, const tf_gpu_frame *frame, int plane,
   DevFrame *d;
   const int num_planes = frame->plane[1] ? 3 : 1;
   if (plane >= num_planes) return fail(ctx, TF_GPU_ERR_INVALID, "plane not present");
+  if (ctx->done_valid) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev, 0));
   int rc = get_frame(ctx, frame, num_planes, &d);
   if (rc) return rc;
+  CU(cudaStreamWaitEvent(ctx->stream, d->ready, 0));
   const Geometry &g = d->g;
   const int k = plane > 0;
   const int w = g.crop_w[k], h = g.crop_h[k];
