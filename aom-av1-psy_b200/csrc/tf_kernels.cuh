@@ -443,7 +443,7 @@ template <typename T, int W, bool SKIP>
 __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start, int search_step, int *num00,
                                                 MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
-  constexpr int PU = L::MAXP < 3 ? L::MAXP : 3;  // passes whose loads are issued back to back
+  constexpr int PU = (W == 32) ? 2 : (L::MAXP < 3 ? L::MAXP : 3);  // passes whose loads are issued back to back
   const Search<T> S = S_in;
   const int lane = lane_id();
   const int grp = lane / L::LPC, row = (lane % L::LPC) * L::RSTEP;
@@ -1011,7 +1011,7 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
 // Kernel 1: the 32x32 search of every frame of the window, chained through
 // ref_mv (temporal_filter.c:855-871).  One warp per 32x32 block.
 template <typename T>
-__global__ void __launch_bounds__(32) tf_search32_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(32, 16) tf_search32_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id();
   const int mb_row = P.row_begin + blockIdx.x / P.mb_cols;
