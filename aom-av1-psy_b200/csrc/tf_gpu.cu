@@ -576,8 +576,12 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   if (slots < TF_GPU_MAX_FRAMES) slots = TF_GPU_MAX_FRAMES;
   ctx->cache.resize(slots);
   cudaError_t e = cudaSetDevice(dev);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  // the ref_mv chain on the main stream is the critical path: give it priority over the
+  // independent 16x16 searches that fill the machine underneath it
+  int prio_lo = 0, prio_hi = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming);
   for (auto &d : ctx->cache)
