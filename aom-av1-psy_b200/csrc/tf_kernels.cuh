@@ -272,6 +272,39 @@ __device__ __forceinline__ unsigned sad_partial(const SadSrc &Q, const unsigned 
   return s;
 }
 
+// Same, for candidates inside the shared-memory window: 32-bit shared addresses and
+// ld.shared (no generic-address descriptor traffic), branch-free.
+__device__ __forceinline__ uint32_t lds_u32(unsigned addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <typename T, int W, bool SKIP>
+__device__ __forceinline__ unsigned sad_partial_win(unsigned win_origin /* shared addr of MV (0,0), row 0 */,
+                                                    int wpitch, int r, int c, int row,
+                                                    const uint32_t (&sw)[SadL<T, W, SKIP>::NW]) {
+  using L = SadL<T, W, SKIP>;
+  const unsigned a = win_origin + (unsigned)((r + row) * wpitch + c * (int)sizeof(T));
+  const unsigned wa = a & ~3u, sh = (a & 3u) * 8;
+  uint32_t w[L::NW + 1];
+#pragma unroll
+  for (int j = 0; j <= L::NW; j++) w[j] = lds_u32(wa + 4 * j);
+  unsigned s = 0;
+  if (sizeof(T) == 1) {
+#pragma unroll
+    for (int j = 0; j < L::NW; j++) s = __vsadu4(__funnelshift_r(w[j], w[j + 1], sh), sw[j]) + s;
+  } else {
+    unsigned acc = 0;
+#pragma unroll
+    for (int j = 0; j < L::NW; j++) {
+      const unsigned x = __funnelshift_r(w[j], w[j + 1], sh);
+      acc += __vmaxu2(x, sw[j]) - __vminu2(x, sw[j]);
+    }
+    s = (acc & 0xffffu) + (acc >> 16);
+  }
+  return s;
+}
+
 // mvsad_err_cost (mcomp.c:310-331), L1, ref = 0
 template <typename T>
 __device__ __forceinline__ int sad_cost(const Search<T> &S, int r, int c) {
@@ -283,7 +316,7 @@ __device__ __forceinline__ int sse_cost(const Search<T> &S, int r8, int c8) {
   return (S.sse_lambda * (iabs(r8) + iabs(c8))) >> 3;
 }
 __device__ __forceinline__ bool in_range(const Lim &l, int r, int c) {
-  return c >= l.col_min && c <= l.col_max && r >= l.row_min && r <= l.row_max;
+  return (c >= l.col_min) & (c <= l.col_max) & (r >= l.row_min) & (r <= l.row_max);  // branch-free
 }
 template <bool SKIP>
 __device__ __forceinline__ unsigned sad_post(unsigned s, int hbd_shift) {
@@ -469,7 +502,8 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
                         (best.col - rad >= S.lim.col_min) && (best.col + rad <= S.lim.col_max);
     unsigned mykey = 0xffffffffu;
     if (window_covers(S, best.row, best.col, rad)) {
-      const SadSrc Q = sad_src(S, true);
+      const unsigned worg = (unsigned)__cvta_generic_to_shared(S.win) +
+                            (unsigned)((S.wR - S.wr) * S.wpitch + (S.wR - S.wc) * (int)sizeof(T) + S.wshift);
 #pragma unroll 1
       for (int p0 = 0; p0 * L::CPP < nsites; p0 += PU) {
         unsigned part[PU];
@@ -479,12 +513,13 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
         for (int u = 0; u < PU; u++) {  // independent loads + partial SADs
           const int idx = 1 + (p0 + u) * L::CPP + grp;
           const bool live = idx <= nsites;
-          const int my_r = best.row + c_sites.r[step][live ? idx : 0];
-          const int my_c = best.col + c_sites.c[step][live ? idx : 0];
+          const int sidx = live ? idx : 0;  // site 0 = the centre: always inside the window
+          const int my_r = best.row + c_sites.r[step][sidx];
+          const int my_c = best.col + c_sites.c[step][sidx];
           cost[u] = sad_cost(S, my_r, my_c);
           // exact pruning: a site is accepted only if sad + cost < bestsad and sad >= 0
-          ok[u] = live && (all_in || in_range(S.lim, my_r, my_c)) && (unsigned)cost[u] < bestsad;
-          part[u] = sad_partial<T, W, SKIP>(Q, safe, my_r, my_c, row, ok[u], sw);
+          ok[u] = live & (all_in | in_range(S.lim, my_r, my_c)) & ((unsigned)cost[u] < bestsad);
+          part[u] = sad_partial_win<T, W, SKIP>(worg, S.wpitch, my_r, my_c, row, sw);
         }
 #pragma unroll
         for (int u = 0; u < PU; u++) {
