@@ -28,7 +28,7 @@ EXPORTS = [
     "tf_gpu_filter", "tf_gpu_filter_dump", "tf_gpu_submit", "tf_gpu_wait", "tf_gpu_cache_frame",
     "tf_gpu_evict_frame", "tf_gpu_filter_resident", "tf_gpu_download_output", "tf_gpu_output_device_plane",
     "tf_gpu_host_register", "tf_gpu_host_unregister", "tf_gpu_last_stats", "tf_gpu_event_record",
-    "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench", "tf_gpu_last_kernel_times",
+    "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench", "tf_gpu_last_kernel_times", "tf_gpu_filter_resident_async", "tf_gpu_filter_resident_result",
 ]
 
 
@@ -97,6 +97,8 @@ def load_library():
     lib.tf_gpu_filter_resident.argtypes = [vp, C.POINTER(Params), C.POINTER(u64), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_float)]
     lib.tf_gpu_download_output.argtypes = [vp, C.POINTER(Frame), i, i]
+    lib.tf_gpu_filter_resident_async.argtypes = [vp, C.POINTER(Params), C.POINTER(u64)]
+    lib.tf_gpu_filter_resident_result.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_float)]
     lib.tf_gpu_output_device_plane.argtypes = [vp, i, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(i),
                                                C.POINTER(i)]
     lib.tf_gpu_host_register.argtypes = [vp, vp, C.c_size_t]
@@ -294,6 +296,17 @@ class TemporalFilterGpu:
         diff = (C.c_int64 * 2)()
         ms = C.c_float()
         self._check(self.lib.tf_gpu_filter_resident(self.h, C.byref(cp), ids, diff, C.byref(ms)))
+        return ms.value, np.array([diff[0], diff[1]], np.int64)
+
+    def filter_resident_async(self, params, frame_ids):
+        cp = make_params(params) if isinstance(params, dict) else params
+        ids = (C.c_uint64 * len(frame_ids))(*frame_ids)
+        self._check(self.lib.tf_gpu_filter_resident_async(self.h, C.byref(cp), ids))
+
+    def filter_resident_result(self):
+        diff = (C.c_int64 * 2)()
+        ms = C.c_float()
+        self._check(self.lib.tf_gpu_filter_resident_result(self.h, diff, C.byref(ms)))
         return ms.value, np.array([diff[0], diff[1]], np.int64)
 
     def download_output(self, out, row_begin=0, row_end=0):

@@ -194,14 +194,24 @@ int get_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *f, int num_planes, DevFrame *
   if (!make_geometry(f, num_planes, &g)) return fail(ctx, TF_GPU_ERR_INVALID, "bad frame geometry");
   DevFrame *d = find_cached(ctx, f->frame_id, &g);
   if (!d) {
+    // Victim choice, cheapest first: an allocated slot of the same geometry that holds nothing
+    // (or an uncached scratch frame, id 0), then a never-allocated slot, then plain LRU.
+    // Reusing allocations keeps cudaMalloc (device-synchronising) out of the steady state.
     DevFrame *victim = nullptr;
+    int best_score = 99;
     for (auto &s : ctx->cache) {
       if (s.pinned_epoch == ctx->epoch) continue;
-      if (!s.valid) {
+      const bool same = s.base[0] && s.g == g;
+      int score;
+      if (!s.valid && same) score = 0;
+      else if (s.valid && s.frame_id == 0 && same) score = 1;
+      else if (!s.valid) score = 2;
+      else if (s.frame_id == 0) score = 3;
+      else score = 4;
+      if (score < best_score || (score == best_score && victim && s.last_use < victim->last_use)) {
+        best_score = score;
         victim = &s;
-        break;
       }
-      if (!victim || s.last_use < victim->last_use) victim = &s;
     }
     if (!victim) return fail(ctx, TF_GPU_ERR_MEM, "frame cache too small for this window");
     int rc = alloc_dev_frame(ctx, victim, g);
@@ -751,8 +761,7 @@ int tf_gpu_filter(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_fra
   return tf_gpu_filter_dump(ctx, params, frames, out, diff_sum_sse, nullptr);
 }
 
-int tf_gpu_filter_resident(tf_gpu_ctx *ctx, const tf_gpu_params *params, const uint64_t *frame_ids,
-                           int64_t diff_sum_sse[2], float *time_ms) {
+int tf_gpu_filter_resident_async(tf_gpu_ctx *ctx, const tf_gpu_params *params, const uint64_t *frame_ids) {
   if (!ctx || !frame_ids) return TF_GPU_ERR_INVALID;
   int rc = validate_params(ctx, params);
   if (rc) return rc;
@@ -775,6 +784,12 @@ int tf_gpu_filter_resident(tf_gpu_ctx *ctx, const tf_gpu_params *params, const u
   rc = launch_filter(ctx, params, devf, g, ctx->d_diff, nullptr, true);
   if (rc) return rc;
   CU(cudaMemcpyAsync(ctx->h_diff, ctx->d_diff, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_filter_resident_result(tf_gpu_ctx *ctx, int64_t diff_sum_sse[2], float *time_ms) {
+  if (!ctx) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
   if (diff_sum_sse) {
     diff_sum_sse[0] = (int64_t)ctx->h_diff[0];
@@ -785,6 +800,13 @@ int tf_gpu_filter_resident(tf_gpu_ctx *ctx, const tf_gpu_params *params, const u
   ctx->last_kernel_ms = ms;
   if (time_ms) *time_ms = ms;
   return TF_GPU_OK;
+}
+
+int tf_gpu_filter_resident(tf_gpu_ctx *ctx, const tf_gpu_params *params, const uint64_t *frame_ids,
+                           int64_t diff_sum_sse[2], float *time_ms) {
+  const int rc = tf_gpu_filter_resident_async(ctx, params, frame_ids);
+  if (rc) return rc;
+  return tf_gpu_filter_resident_result(ctx, diff_sum_sse, time_ms);
 }
 
 int tf_gpu_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, int row_begin, int row_end) {

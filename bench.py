@@ -9,8 +9,10 @@ per GPU (mode windows, weak scaling: independent windows per GPU, no collective)
 one window sharded by 32-px block rows over all GPUs and gathered with NCCL (mode
 slab, strong scaling).  Prints ONE JSON line (rank 0).
 
- value     frames/s with the window resident in HBM (device-event time of K steps on the
-           library's own stream, max over ranks)
+ value     frames/s with the windows resident in HBM (device-event time of K steps on the
+           library's own streams, max over ranks).  A step filters `windows_in_flight_per_gpu`
+           independent windows per GPU concurrently (one tf_gpu context each; SURVEY 8e config 5:
+           batches of independent ARF windows): 2 at 4K, 4 at 1080p, 1 in slab mode
  e2e       the same through tf_gpu_filter() with HOST (pinned) buffers: H2D of all window
            frames + D2H of the filtered frame inside the timed region, every step
  roofline  HBM view of the block kernel (algorithmic bytes = (N+1) planes per launch) plus
@@ -92,7 +94,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -231,13 +233,15 @@ def run_reference_arm(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="4k10_n15", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="windows", choices=["windows", "slab"])
     ap.add_argument("--impl", default="tfgpu", choices=["tfgpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--concurrent", type=int, default=0,
+                    help="independent windows in flight per GPU (contexts); 0 = auto: 2 for 4K, 4 below")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "tfgpu" else args.warmup
     wl = args.workload
@@ -260,9 +264,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     pkg = load_package()
-    ctx = pkg.TemporalFilterGpu(device=local, max_cached_frames=40)
-
     width, height, bd, n, strength = WORKLOADS[wl]
+    slab_req = args.mode == "slab" and world > 1
+    conc = args.concurrent if args.concurrent > 0 else (1 if slab_req else (2 if width >= 3000 else 4))
+    ctxs = [pkg.TemporalFilterGpu(device=local, max_cached_frames=40) for _ in range(conc)]
+    ctx = ctxs[0]
+
     use_hbd = bd > 8
     mb_rows, mb_cols = (height + 31) // 32, (width + 31) // 32
     p = _params.tf_params(width, height, n, bit_depth=bd, q_factor=Q_FACTOR, filter_strength=strength)
@@ -272,18 +279,24 @@ def main():
     nwin = max(2, int(np.ceil(400e6 / win_bytes)))
     nwin = min(nwin, 40 // n) if 40 // n >= 1 else 1
     slab = args.mode == "slab" and world > 1
-    windows = []
-    for w in range(nwin):
-        seed = (77 if bd > 8 else 1234) + (0 if slab else 1000 * rank) + w
-        frames = make_window(width, height, bd, n, seed)
-        bufs = []
-        for i, (y, u, v) in enumerate(frames):
-            b = pkg.Yv12Buffer(width, height, 1, 1, use_hbd, p["border"], frame_id=1 + w * 100 + i)
-            b.set_planes(y, u, v, extend=False)
-            for a in b.alloc:
-                ctx.host_register(a)
-            bufs.append(b)
-        windows.append((frames, bufs))
+    if conc > 1:
+        nwin = max(2, int(np.ceil(nwin / conc)))
+    all_windows = []  # [context][window] -> (frames, bufs)
+    for ci in range(conc):
+        windows = []
+        for w in range(nwin):
+            seed = (77 if bd > 8 else 1234) + (0 if slab else 1000 * rank) + 100 * ci + w
+            frames = make_window(width, height, bd, n, seed)
+            bufs = []
+            for i, (y, u, v) in enumerate(frames):
+                b = pkg.Yv12Buffer(width, height, 1, 1, use_hbd, p["border"], frame_id=1 + w * 100 + i)
+                b.set_planes(y, u, v, extend=False)
+                for a in b.alloc:
+                    ctxs[ci].host_register(a)
+                bufs.append(b)
+            windows.append((frames, bufs))
+        all_windows.append(windows)
+    windows = all_windows[0]
     out = pkg.Yv12Buffer(width, height, 1, 1, use_hbd, p["border"])
     for a in out.alloc:
         ctx.host_register(a)
@@ -291,9 +304,10 @@ def main():
     # noise levels of the frame to filter (tf_setup_filtering_buffer, temporal_filter.c:1023-1027)
     fi = p["filter_frame_idx"]
     p["noise_levels"] = tuple(ctx.estimate_noise_from_single_plane(windows[0][1][fi], pl, bd) for pl in range(3))
-    for _, bufs in windows:
-        for b in bufs:
-            ctx.cache_frame(b)
+    for ci in range(conc):
+        for _, bufs in all_windows[ci]:
+            for b in bufs:
+                ctxs[ci].cache_frame(b)
 
     if slab:
         r0 = (mb_rows * rank) // world
@@ -301,7 +315,8 @@ def main():
         p["out_row_begin"], p["out_row_end"] = r0, r1
 
     def barrier():
-        ctx.synchronize()
+        for c in ctxs:
+            c.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -339,11 +354,18 @@ def main():
     ktimes = [0.0, 0.0, 0.0]
 
     def step(k):
+        """One step = one window per context, all contexts of this GPU in flight together."""
         nonlocal launches, ktimes
-        ms, diff = ctx.filter_resident(p, ids[k % nwin])
-        launches += ctx.last_stats()[0]
-        for i, t in enumerate(ctx.last_kernel_times()):
-            ktimes[i] += t
+        for c in ctxs:
+            c.filter_resident_async(p, ids[k % nwin])
+        ms = 0.0
+        for ci, c in enumerate(ctxs):
+            m, diff = c.filter_resident_result()
+            ms = max(ms, m)
+            launches += c.last_stats()[0]
+            if ci == 0:
+                for i, t in enumerate(c.last_kernel_times()):
+                    ktimes[i] += t
         if slab:
             slab_gather(diff)
         return ms
@@ -355,13 +377,15 @@ def main():
     sampler.start()
     launches = 0
     ktimes = [0.0, 0.0, 0.0]
-    ctx.event_record(0)
+    for c in ctxs:
+        c.event_record(0)
     t0 = time.perf_counter()
     kernel_ms = 0.0
     for k in range(args.steps):
         kernel_ms += step(k)
-    ctx.event_record(1)
-    dev_ms = ctx.event_elapsed_ms(0, 1)
+    for c in ctxs:
+        c.event_record(1)
+    dev_ms = max(c.event_elapsed_ms(0, 1) for c in ctxs)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
@@ -370,21 +394,34 @@ def main():
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tot_ms, kern_ms_max = tmax.tolist()
-    frames_done = args.steps * (1 if slab else world)
+    frames_done = args.steps * (1 if slab else world * conc)
     value = frames_done / (tot_ms * 1e-3)
 
     # ---- e2e: host buffers through tf_gpu_filter, copies inside the timed region --------
     e2e = None
     if not args.no_e2e and not slab:
-        for _, bufs in windows:
-            for b in bufs:
-                b.frame_id = 0  # never cached: every step uploads the whole window
+        outs = [out]
+        for ci in range(1, conc):
+            o = pkg.Yv12Buffer(width, height, 1, 1, use_hbd, p["border"])
+            for a in o.alloc:
+                ctxs[ci].host_register(a)
+            outs.append(o)
+        for ci in range(conc):
+            for _, bufs in all_windows[ci]:
+                for b in bufs:
+                    b.frame_id = 0  # never cached: every step uploads the whole window
+
+        def e2e_step(k):
+            tk = [ctxs[ci].submit(p, all_windows[ci][k % nwin][1], outs[ci]) for ci in range(conc)]
+            for ci, (t, _diff, _keep) in enumerate(tk):
+                ctxs[ci].wait(t)
+
         for k in range(2):
-            ctx.temporal_filter(p, windows[k % nwin][1], out)
+            e2e_step(k)
         barrier()
         t0 = time.perf_counter()
         for k in range(args.steps):
-            ctx.temporal_filter(p, windows[k % nwin][1], out)
+            e2e_step(k)
         barrier()
         e_ms = (time.perf_counter() - t0) * 1e3
         te = torch.tensor([e_ms], device=f"cuda:{local}", dtype=torch.float64)
@@ -392,8 +429,8 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         es = 2 if use_hbd else 1
         d2h = sum(out.full_blocks(pl).size for pl in range(3)) * es
-        e2e = {"value": args.steps * world / (te.item() * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": plane_bytes(width, height, bd) * n, "d2h_bytes_per_step": int(d2h)}
+        e2e = {"value": args.steps * world * conc / (te.item() * 1e-3), "unit": "frames/s",
+               "h2d_bytes_per_step": plane_bytes(width, height, bd) * n * conc, "d2h_bytes_per_step": int(d2h) * conc}
 
     if rank != 0:
         if world > 1:
@@ -456,6 +493,7 @@ def main():
                    "num_frames": n, "filter_strength": strength, "q_factor": Q_FACTOR,
                    "speed_class": "good cpu-used=4 (PRUNED_MORE, prune mesh lvl2, skip-row SAD)",
                    "mode": "slab rows + NCCL gather" if slab else "independent windows per GPU",
+                   "windows_in_flight_per_gpu": conc,
                    "l2": f"inputs larger than L2: {nwin} resident windows x {win_bytes / 1e6:.0f} MB cycled",
                    "timing": "CUDA events on the library stream around K steps, max over ranks"},
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,

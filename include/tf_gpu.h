@@ -157,6 +157,10 @@ int tf_gpu_evict_frame(tf_gpu_ctx *ctx, uint64_t frame_id);
 int tf_gpu_filter_resident(tf_gpu_ctx *ctx, const tf_gpu_params *params,
                            const uint64_t *frame_ids /*[num_frames]*/,
                            int64_t diff_sum_sse[2], float *time_ms);
+/* Asynchronous halves of the above, so that several contexts (independent windows)
+ * can be in flight on one GPU: _async enqueues, _result waits and returns FRAME_DIFF / kernel time. */
+int tf_gpu_filter_resident_async(tf_gpu_ctx *ctx, const tf_gpu_params *params, const uint64_t *frame_ids);
+int tf_gpu_filter_resident_result(tf_gpu_ctx *ctx, int64_t diff_sum_sse[2], float *time_ms);
 int tf_gpu_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, int row_begin, int row_end);
 /* Raw device pointer + pitch (bytes) of an output plane, for NCCL gathers in
  * slab mode (the reference's counterpart is the shared tf_ctx->output_frame
