@@ -28,6 +28,11 @@ CASES = [
     ("intmv10_speed0", 128, 96, 3, 10, {}, dict(force_integer_mv=1, speed=0)),
     ("hd720_8_skip", 1280, 720, 3, 8, {}, {}),
     ("hd720_10_skip", 1280, 720, 3, 10, dict(motion=(2, 7)), {}),
+    ("tiny_40x24", 40, 24, 3, 8, {}, {}),
+    ("tiny_17x33_10", 17, 33, 3, 10, {}, dict(speed=1)),
+    ("i444_12_speed0", 72, 40, 3, 12, {}, dict(ss_x=0, ss_y=0, speed=0)),
+    ("hd720_8_noskip_speed2", 736, 720, 2, 8, dict(motion=(1, 3)), dict(speed=2, use_downsampled_sad=0)),
+    ("long_window_21", 96, 64, 21, 8, dict(motion=(0, 1)), dict(filter_frame_idx=10)),
 ]
 
 
