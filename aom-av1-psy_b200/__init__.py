@@ -28,7 +28,7 @@ EXPORTS = [
     "tf_gpu_filter", "tf_gpu_filter_dump", "tf_gpu_submit", "tf_gpu_wait", "tf_gpu_cache_frame",
     "tf_gpu_evict_frame", "tf_gpu_filter_resident", "tf_gpu_download_output", "tf_gpu_output_device_plane",
     "tf_gpu_host_register", "tf_gpu_host_unregister", "tf_gpu_last_stats", "tf_gpu_event_record",
-    "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench", "tf_gpu_last_kernel_times", "tf_gpu_filter_resident_async", "tf_gpu_filter_resident_result",
+    "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench", "tf_gpu_last_kernel_times", "tf_gpu_filter_resident_async", "tf_gpu_filter_resident_result", "tf_gpu_collect_counters", "tf_gpu_read_counters",
 ]
 
 
@@ -109,6 +109,8 @@ def load_library():
     lib.tf_gpu_synchronize.argtypes = [vp]
     lib.tf_gpu_microbench.argtypes = [vp, i, C.POINTER(C.c_double)]
     lib.tf_gpu_last_kernel_times.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.tf_gpu_collect_counters.argtypes = [vp, i]
+    lib.tf_gpu_read_counters.argtypes = [vp, C.POINTER(u64)]
     _lib = lib
     return lib
 
@@ -340,6 +342,14 @@ class TemporalFilterGpu:
         v = C.c_double()
         self._check(self.lib.tf_gpu_microbench(self.h, kind, C.byref(v)))
         return v.value
+
+    def collect_counters(self, enable):
+        self._check(self.lib.tf_gpu_collect_counters(self.h, int(enable)))
+
+    def read_counters(self):
+        c = (C.c_uint64 * 4)()
+        self._check(self.lib.tf_gpu_read_counters(self.h, c))
+        return [int(x) for x in c]
 
     def last_kernel_times(self):
         ms = (C.c_float * 3)()

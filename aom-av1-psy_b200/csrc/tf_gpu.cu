@@ -76,6 +76,9 @@ struct tf_gpu_ctx {
   unsigned long long *d_diff = nullptr;   // [8][2] ring
   unsigned long long *h_diff = nullptr;   // pinned mirror
   unsigned long long *d_noise = nullptr;  // [2]
+  unsigned long long *d_ctr = nullptr;    // [4] executed-work counters (instrumentation)
+  unsigned long long h_ctr[4] = { 0, 0, 0, 0 };
+  bool collect_counters = false;
   unsigned long long *h_noise = nullptr;
   Ticket tickets[8];
   uint64_t next_ticket = 1;
@@ -374,6 +377,11 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     for (int pl = 0; pl < p->num_planes; pl++) K.frm[f][pl] = frames[f]->p00[pl];
   for (int pl = 0; pl < p->num_planes; pl++) K.out[pl] = ctx->out.p00[pl];
   K.diff = d_diff;
+  K.ctr = nullptr;
+  if (ctx->collect_counters) {
+    K.ctr = ctx->d_ctr;
+    CU(cudaMemsetAsync(ctx->d_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  }
   K.num_pels = 1024 + (p->num_planes > 1 ? 2 * (1024 >> (g.ss_x + g.ss_y)) : 0);
   K.row_begin = 0;
   K.row_end = K.mb_rows;
@@ -607,6 +615,7 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_diff, 16 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_diff, 16 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_noise, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctr, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_noise, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) {
     Sites s;
@@ -644,6 +653,7 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
   if (ctx->d_diff) cudaFree(ctx->d_diff);
   if (ctx->h_diff) cudaFreeHost(ctx->h_diff);
   if (ctx->d_noise) cudaFree(ctx->d_noise);
+  if (ctx->d_ctr) cudaFree(ctx->d_ctr);
   if (ctx->h_noise) cudaFreeHost(ctx->h_noise);
   for (int i = 0; i < 8; i++)
     if (ctx->tickets[i].ev) cudaEventDestroy(ctx->tickets[i].ev);
@@ -850,6 +860,21 @@ int tf_gpu_host_unregister(tf_gpu_ctx *ctx, void *ptr) {
   if (!ctx || !ptr) return TF_GPU_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
   CU(cudaHostUnregister(ptr));
+  return TF_GPU_OK;
+}
+
+int tf_gpu_collect_counters(tf_gpu_ctx *ctx, int enable) {
+  if (!ctx) return TF_GPU_ERR_INVALID;
+  ctx->collect_counters = enable != 0;
+  return TF_GPU_OK;
+}
+
+int tf_gpu_read_counters(tf_gpu_ctx *ctx, uint64_t counters[4]) {
+  if (!ctx || !counters) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpy(ctx->h_ctr, ctx->d_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; i++) counters[i] = ctx->h_ctr[i];
   return TF_GPU_OK;
 }
 

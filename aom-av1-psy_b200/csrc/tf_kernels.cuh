@@ -65,6 +65,7 @@ struct KParams {
   void *out[3];
   int out_pitch[2];
   unsigned long long *diff;  // [2]
+  unsigned long long *ctr;   // [4] optional executed-work counters, see Search::ctr
   // optional dumps (device)
   int16_t *d_mvs;
   int32_t *d_mses;
@@ -132,6 +133,9 @@ struct Search {
   int wr, wc, wR;
   int wpitch;  // bytes; wpitch/4 is odd
   int wshift;  // bytes the window origin was aligned down by
+  // optional executed-work counters (bench instrumentation; nullptr in normal runs):
+  // [0] SAD sample pairs read, [1] sub-pel candidate evaluations x block samples, [2] variance samples
+  unsigned long long *ctr;
 };
 
 constexpr int WIN_BYTES = 12288;  // window capacity per warp, 32x32 search
@@ -457,6 +461,7 @@ template <typename T, int W>
 __device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
   unsigned sse;
   const int v = (int)variance<T, W>(S.src, S.stride, S.ref + r * S.stride + c, S.stride, S.hbd_shift, &sse);
+  if (S.ctr && lane_id() == 0) atomicAdd(&S.ctr[2], (unsigned long long)(W * W));
   return v + sse_cost(S, r * 8, c * 8);
 }
 
@@ -492,6 +497,7 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
   MV2 best = start;
   unsigned bestsad = sad_single<T, W, SKIP>(S, start.row, start.col, lane, sw) + sad_cost(S, start.row, start.col);
   int is_off_center = 0;
+  unsigned ncand = 1;  // candidates whose samples were read (instrumentation)
   int next_step_size = tot_steps > 2 ? c_sites.radius[tot_steps - 2] : 1;
   for (int step = tot_steps - 1; step >= 0; --step) {
     if (step > 0) next_step_size = c_sites.radius[step - 1];
@@ -521,6 +527,7 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
           ok[u] = live & (all_in | in_range(S.lim, my_r, my_c)) & ((unsigned)cost[u] < bestsad);
           part[u] = sad_partial_win<T, W, SKIP>(worg, S.wpitch, my_r, my_c, row, sw);
         }
+        ncand += imin(PU * L::CPP, nsites - p0 * L::CPP);
 #pragma unroll
         for (int u = 0; u < PU; u++) {
           const unsigned tot = sad_post<SKIP>(seg_reduce_u32<L::LPC>(part[u]), S.hbd_shift) + (unsigned)cost[u];
@@ -544,6 +551,7 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
           // exact pruning: sad + cost < bestsad is impossible once cost >= bestsad
           okv[u] = (all_in || in_range(S.lim, cr, cc)) && cst[u] < bestsad;
           any_ok |= okv[u];
+          ncand += okv[u];
           part[u] = okv[u] ? far_partial<T, W, SKIP>(S.ref, S.stride, cr, cc, lane, sf) : 0u;
         }
         if (!any_ok) continue;
@@ -578,6 +586,7 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
       }
     }
   }
+  if (S.ctr && lane == 0) atomicAdd(&S.ctr[0], (unsigned long long)ncand * (L::ROWS * W));
   *num00 = n00;
   *best_out = best;
   return bestsad;
@@ -684,6 +693,7 @@ __device__ __noinline__ int mesh_search(const Search<T> &S_in, MV2 start, int ra
     const unsigned long long other = __shfl_xor_sync(FULL, mykey, o);
     mykey = other < mykey ? other : mykey;
   }
+  if (S.ctr && lane == 0) atomicAdd(&S.ctr[0], (unsigned long long)(total + 1) * (L::ROWS * W));
   if ((unsigned)(mykey >> 32) < best_sad) {
     best_sad = (unsigned)(mykey >> 32);
     const int q = (int)(mykey & 0xffffffffull);
@@ -832,6 +842,7 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
       sse += (unsigned)(d * d);
     }
   }
+  if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(W * W));
   sum = warp_sum_i32(sum);
   const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
   unsigned sse_out;
@@ -894,6 +905,7 @@ __device__ __noinline__ unsigned upsampled_err(const Search<T> &S, int r8, int c
     sse += (unsigned)(d * d);
   }
   __syncwarp();
+  if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(W * W));
   sum = warp_sum_i32(sum);
   const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
   unsigned sse_out;
@@ -1031,6 +1043,7 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
   S.is_hbd = P.is_hbd;
   S.win = nullptr;
   S.wr = S.wc = S.wR = S.wpitch = S.wshift = 0;
+  S.ctr = P.ctr;
   // av1_set_mv_{row,col}_limits (mcomp.h:216-240) + av1_set_mv_search_range (mcomp.c:196-215)
   const int border = P.border, mi_row = mb_row * 8, mi_col = mb_col * 8;
   S.lim.row_min = imax(-(mi_row * 4 + border - 8), -(((mi_row + 8) * 4) + 8));

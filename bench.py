@@ -397,6 +397,12 @@ def main():
     frames_done = args.steps * (1 if slab else world * conc)
     value = frames_done / (tot_ms * 1e-3)
 
+    # executed work of one window (untimed, instrumented): SURVEY 8d "executed op count"
+    ctx.collect_counters(1)
+    ctx.filter_resident(p, ids[0])
+    executed = ctx.read_counters()
+    ctx.collect_counters(0)
+
     # ---- e2e: host buffers through tf_gpu_filter, copies inside the timed region --------
     e2e = None
     if not args.no_e2e and not slab:
@@ -470,7 +476,13 @@ def main():
     r_sad = rates["vabsdiff4"] * 4 if bd == 8 else rates["vimnmx_u16x2"] * 2 / 3
     t_int_block = (W["sad"] / r_sad + (W["var"] + W["subpel"] + W["pred"]) / rates["imad"] + W["weights"] / rates["iadd"]) / 1e9
     t_int = t_int_block * mb_rows * mb_cols * (n - 1) * rows_frac
-    step_alg = (n + 1) * plane_bytes(width, height, bd) * rows_frac
+    step_alg = (n + 1) * plane_bytes(width, height, bd) * rows_frac * conc
+    nbr = mb_rows * mb_cols * (n - 1) * rows_frac
+    w_exec = {"sad": executed[0] / nbr, "subpel": executed[1] * 6 / nbr, "var": executed[2] * 2 / nbr,
+              "pred": W["pred"], "weights": W["weights"]}
+    t_exec = nbr * (w_exec["sad"] / r_sad + (w_exec["var"] + w_exec["subpel"] + w_exec["pred"]) / rates["imad"]
+                    + w_exec["weights"] / rates["iadd"]) / 1e9
+    exec_info = {"work_per_block_ref": w_exec, "t_int_ms": t_exec * conc * 1e3, "frac": t_exec * conc / kern_s}
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "traffic": traffic, "peak_source": peak_src, "kernel": dom_name, "kernel_ms": per_launch_ms[dom_name],
@@ -479,9 +491,11 @@ def main():
         "phases_ms": {"search32_chain_with_search16_overlapped": kt[0], "search16_tail": kt[1], "filter": kt[2]},
         "step": {"algorithmic_bytes": step_alg, "kernels_ms_sum": kern_s * 1e3,
                  "achieved_gbs": step_alg / kern_s / 1e9, "frac": step_alg / kern_s / 1e9 / hbm_peak},
-        "int": {"note": "binding roofline per SURVEY 8d: T_int = sum_class W_class / R_class over measured pipe rates, whole step",
-                "work_per_block_ref": W, "rates_giga_lane_ops_per_s": rates, "t_int_ms": t_int * 1e3,
-                "frac": t_int / kern_s},
+        "int": {"note": "binding roofline per SURVEY 8d: T_int = sum_class W_class / R_class over measured pipe rates, whole "
+                        "step (all windows in flight); W = static-content floor, executed = instrumented counts of this clip",
+                "work_per_block_ref": W, "rates_giga_lane_ops_per_s": rates, "t_int_ms": t_int * conc * 1e3,
+                "frac": t_int * conc / kern_s,
+                "executed": exec_info},
     }
 
     line = {

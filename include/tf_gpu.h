@@ -176,6 +176,12 @@ int tf_gpu_host_unregister(tf_gpu_ctx *ctx, void *ptr);
  * device time (ms) of the block-filter kernel. */
 int tf_gpu_last_stats(const tf_gpu_ctx *ctx, int *kernel_launches, float *filter_kernel_ms);
 
+/* Executed-work instrumentation for the INT roofline (SURVEY 8d "executed op count"): when
+ * enabled, the search kernels count [0] SAD sample pairs read, [1] sub-pel candidate samples,
+ * [2] full-pel variance samples of the next filter call(s).  Off by default (atomics perturb timing). */
+int tf_gpu_collect_counters(tf_gpu_ctx *ctx, int enable);
+int tf_gpu_read_counters(tf_gpu_ctx *ctx, uint64_t counters[4]);
+
 /* Device time (ms) of the three kernels of the last filter call:
  * [0] tf_search32_kernel, [1] tf_search16_kernel, [2] tf_filter_kernel. */
 int tf_gpu_last_kernel_times(tf_gpu_ctx *ctx, float ms[3]);
