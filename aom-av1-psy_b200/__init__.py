@@ -60,7 +60,7 @@ class Params(C.Structure):
         ("allow_hp", C.c_int), ("subpel_method", C.c_int), ("subpel_iters_per_step", C.c_int),
         ("prune_mesh_level", C.c_int), ("mesh_patterns", (C.c_int * 2) * 4), ("use_downsampled_sad", C.c_int),
         ("compute_frame_diff", C.c_int), ("out_row_begin", C.c_int), ("out_row_end", C.c_int),
-        ("reserved", C.c_int * 8),
+        ("extend_output_borders", C.c_int), ("reserved", C.c_int * 7),
     ]
 
 
@@ -210,6 +210,7 @@ def make_params(p):
         c.mesh_patterns[i][0], c.mesh_patterns[i][1] = p["mesh"][i]
     c.use_downsampled_sad, c.compute_frame_diff = p["use_downsampled_sad"], p["compute_frame_diff"]
     c.out_row_begin, c.out_row_end = p.get("out_row_begin", 0), p.get("out_row_end", 0)
+    c.extend_output_borders = p.get("extend_output_borders", 0)
     return c
 
 

@@ -112,7 +112,7 @@ int fail(tf_gpu_ctx *c, int code, const char *fmt, ...) {
 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
-bool make_geometry(const tf_gpu_frame *f, int num_planes, Geometry *g) {
+bool make_geometry(const tf_gpu_frame *f, int num_planes, Geometry *g, int luma_border = DEV_BORDER) {
   memset(g, 0, sizeof(*g));
   g->is_hbd = f->is_hbd ? 1 : 0;
   g->ss_x = f->ss_x;
@@ -127,8 +127,8 @@ bool make_geometry(const tf_gpu_frame *f, int num_planes, Geometry *g) {
   if (f->crop_w[0] <= 0 || f->crop_h[0] <= 0 || f->ss_x < 0 || f->ss_x > 1 || f->ss_y < 0 || f->ss_y > 1) return false;
   if (f->aligned_w[0] < f->crop_w[0] || f->aligned_h[0] < f->crop_h[0]) return false;
   for (int k = 0; k < 2; k++) {
-    g->bx[k] = k ? DEV_BORDER >> f->ss_x : DEV_BORDER;
-    g->by[k] = k ? DEV_BORDER >> f->ss_y : DEV_BORDER;
+    g->bx[k] = k ? luma_border >> f->ss_x : luma_border;
+    g->by[k] = k ? luma_border >> f->ss_y : luma_border;
     g->pitch[k] = align_up(g->aligned_w[k] + 2 * g->bx[k], 128);
     g->rows[k] = g->aligned_h[k] + 2 * g->by[k] + 2;  // + slack rows: window / word over-reads stay inside
   }
@@ -511,6 +511,33 @@ int download_rows(tf_gpu_ctx *ctx, tf_gpu_frame *out, int rb, int re) {
   return TF_GPU_OK;
 }
 
+// aom_extend_frame_borders_c (aom_scale/generic/yv12extend.c:183-223) on the device output, then the
+// whole extended allocation (host border on every side) goes back in one 2-D copy per plane.
+int extend_and_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out) {
+  const Geometry &g = ctx->out.g;
+  const size_t es = g.is_hbd ? 2 : 1;
+  for (int pl = 0; pl < g.num_planes; pl++) {
+    const int k = pl > 0;
+    const int hb_x = k ? out->border >> g.ss_x : out->border, hb_y = k ? out->border >> g.ss_y : out->border;
+    const int ext_w = g.aligned_w[k] + hb_x, ext_h = g.aligned_h[k] + hb_y;  // right / bottom extents from pixel 0
+    const long long n = (long long)(hb_x + ext_w) * (hb_y + ext_h);
+    const int threads = 256;
+    const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads);
+    if (g.is_hbd)
+      extend_borders_kernel<uint16_t><<<blocks, threads, 0, ctx->stream>>>((uint16_t *)ctx->out.p00[pl], g.pitch[k], g.crop_w[k], g.crop_h[k], hb_x, hb_y, ext_w, ext_h);
+    else
+      extend_borders_kernel<uint8_t><<<blocks, threads, 0, ctx->stream>>>((uint8_t *)ctx->out.p00[pl], g.pitch[k], g.crop_w[k], g.crop_h[k], hb_x, hb_y, ext_w, ext_h);
+    ctx->last_launches++;
+    if (!out->plane[pl]) return fail(ctx, TF_GPU_ERR_INVALID, "output plane %d is NULL", pl);
+    char *dst = (char *)out->plane[pl] - ((size_t)hb_y * out->stride[k] + hb_x) * es;
+    const char *src = (const char *)ctx->out.p00[pl] - ((size_t)hb_y * g.pitch[k] + hb_x) * es;
+    CU(cudaMemcpy2DAsync(dst, (size_t)out->stride[k] * es, src, (size_t)g.pitch[k] * es, (size_t)(hb_x + ext_w) * es,
+                         hb_y + ext_h, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaGetLastError());
+  return TF_GPU_OK;
+}
+
 int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame *frames, tf_gpu_frame *out,
                 int64_t diff_sum_sse[2], const tf_gpu_dump *dump, uint64_t *ticket_out) {
   if (!ctx) return TF_GPU_ERR_INVALID;
@@ -535,7 +562,19 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
     if (!(devf[i]->g == devf[0]->g)) return fail(ctx, TF_GPU_ERR_INVALID, "frames of one window must share geometry");
   const Geometry &g = devf[0]->g;
   if (g.is_hbd == 0 && params->bit_depth != 8) return fail(ctx, TF_GPU_ERR_INVALID, "8-bit container needs bit_depth 8");
-  rc = alloc_dev_frame(ctx, &ctx->out, g);
+  Geometry og = g;
+  const bool extend_out = params->extend_output_borders && !(params->out_row_end > params->out_row_begin);
+  if (extend_out) {
+    // the output frame carries the host's full border so the extended allocation can be returned
+    const int ob = ((out->border > DEV_BORDER ? out->border : DEV_BORDER) + 15) & ~15;
+    if (!make_geometry(out, params->num_planes, &og, ob)) return fail(ctx, TF_GPU_ERR_INVALID, "bad output geometry");
+    if (!(og.crop_w[0] == g.crop_w[0] && og.crop_h[0] == g.crop_h[0] && og.is_hbd == g.is_hbd && og.ss_x == g.ss_x && og.ss_y == g.ss_y))
+      return fail(ctx, TF_GPU_ERR_INVALID, "output frame does not match the window geometry");
+    for (int k = 0; k < 2; k++)
+      if (out->stride[k] < og.aligned_w[k] + 2 * (k ? out->border >> og.ss_x : out->border))
+        return fail(ctx, TF_GPU_ERR_INVALID, "output stride too small for its border");
+  }
+  rc = alloc_dev_frame(ctx, &ctx->out, og);
   if (rc) return rc;
   Ticket &t = ctx->tickets[ctx->next_ticket % 8];
   if (t.pending) return fail(ctx, TF_GPU_ERR_INVALID, "too many submits in flight (max 8)");
@@ -550,8 +589,13 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
     rb = params->out_row_begin < 0 ? 0 : params->out_row_begin;
     re = params->out_row_end > mb_rows ? mb_rows : params->out_row_end;
   }
-  rc = download_rows(ctx, out, rb, re);
-  if (rc) return rc;
+  if (extend_out) {
+    rc = extend_and_download_output(ctx, out);
+    if (rc) return rc;
+  } else {
+    rc = download_rows(ctx, out, rb, re);
+    if (rc) return rc;
+  }
   if (dump) {
     rc = download_dump(ctx, params, g, dump);
     if (rc) return rc;

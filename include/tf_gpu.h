@@ -90,7 +90,11 @@ typedef struct {
   int use_downsampled_sad; /* sf.mv_sf.use_downsampled_sad */
   int compute_frame_diff;  /* frame_diff != NULL (:1283) */
   int out_row_begin, out_row_end; /* slab mode: 32-px block rows [begin,end); 0,0 = all rows */
-  int reserved[8];
+  /* 1: also run aom_extend_frame_borders (aom_scale/generic/yv12extend.c:221; called right after
+   * av1_temporal_filter at temporal_filter.c:1372, encode_strategy.c:822) on the device and return the
+   * whole extended allocation of `out` (needs out->border and out->stride to describe it). */
+  int extend_output_borders;
+  int reserved[7];
 } tf_gpu_params;
 
 /* Per-(block, frame) intermediate state for parity tests (what a debug build of

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(pkg):
 def test_struct_layouts(pkg):
     # POD layout the C side compiles to (x86-64 SysV): catches drift between header and binding
     assert C.sizeof(pkg.Frame) == 88
-    assert C.sizeof(pkg.Params) == 160
+    assert C.sizeof(pkg.Params) == 160  # extend_output_borders took one reserved slot
     assert C.sizeof(pkg.Dump) == 40
     assert C.sizeof(pkg.DeviceCfg) == 32
 

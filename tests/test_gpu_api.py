@@ -136,3 +136,30 @@ def test_single_frame_window_is_identity(pkg, tfgpu):
     g = _gpu.run_gpu(pkg, tfgpu, p, frames, dump=False)
     assert (g["out"][0][:H, :W] == frames[0][0]).all()
     assert (g["diff"] == 0).all()
+
+
+@pytest.mark.parametrize("case", [(352, 288, 8, 96), (200, 120, 10, 160), (131, 77, 8, 160)])
+def test_output_border_extension_matches_reference(pkg, tfgpu, case):
+    """aom_extend_frame_borders (yv12extend.c:221), which the caller runs
+    right after av1_temporal_filter (temporal_filter.c:1372), done on the device; the whole extended
+    allocation must equal the reference's."""
+    import _ref
+    if not _ref.available():
+        pytest.skip("oracle/_ref/libtf_ref.so not built")
+    W, H, bd, border = case
+    N = 3
+    frames = _clips.moving_texture(W, H, N, bd)
+    p = _params.tf_params(W, H, N, bit_depth=bd, border=border)
+    r = _ref.RefFilter(p, frames)
+    p["noise_levels"] = tuple(r.estimate_noise())
+    r.close()
+    r = _ref.RefFilter(p, frames)
+    r.run(record=False)
+    _ref.lib().tfref_extend_output_borders(r.h)
+    out = pkg.Yv12Buffer(W, H, 1, 1, p["use_hbd"], border)
+    tfgpu.temporal_filter(dict(p, extend_output_borders=1), _bufs(pkg, p, frames, 0), out)
+    for pl in range(3):
+        ref_plane, _ = r.plane_with_border(-1, pl)
+        assert ref_plane.shape == out.alloc[pl].shape
+        assert (ref_plane == out.alloc[pl]).all(), pl
+    r.close()
