@@ -418,6 +418,34 @@ __device__ __forceinline__ unsigned far_partial(const T *ref, int stride, int r,
   return s;
 }
 
+// Same, with the candidate given as a byte offset from a per-lane base pointer
+// (base = ref + this lane's row offset + word column), so the per-candidate address
+// arithmetic is one 64-bit add.
+template <typename T, int W, bool SKIP>
+__device__ __forceinline__ unsigned far_partial_off(const unsigned char *lane_base, int off, int stride,
+                                                    const uint32_t (&sf)[FarL<T, W, SKIP>::IT]) {
+  using F = FarL<T, W, SKIP>;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(lane_base + off);
+  const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+  const unsigned sh = (unsigned)(a & 3) * 8;
+  const int step_words = F::RPI * F::RSTEP * stride * (int)sizeof(T) / 4;
+  uint32_t w0[F::IT], w1[F::IT];
+#pragma unroll
+  for (int it = 0; it < F::IT; it++) {
+    w0[it] = __ldg(wp + it * step_words);
+    w1[it] = __ldg(wp + it * step_words + 1);
+  }
+  unsigned s = 0;
+#pragma unroll
+  for (int it = 0; it < F::IT; it++) {
+    const unsigned x = __funnelshift_r(w0[it], w1[it], sh);
+    if (sizeof(T) == 1) s = __vsadu4(x, sf[it]) + s;
+    else s += __vmaxu2(x, sf[it]) - __vminu2(x, sf[it]);
+  }
+  if (sizeof(T) != 1) s = (s & 0xffffu) + (s >> 16);
+  return s;
+}
+
 // ---------------------------------------------------------------------------
 // Variance (aom_dsp/variance.c:56-72,141-148; hbd :342-429).  a - b, W x W.
 // Lane = column (W == 32) or (row half, column) (W == 16).
@@ -490,6 +518,9 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
   sad_load_src<T, W, SKIP>(S.src, S.stride, sw);
   uint32_t sf[FarL<T, W, SKIP>::IT];
   far_load_src<T, W, SKIP>(S.src, S.stride, lane, sf);
+  // this lane's row / word position inside a far candidate (row-major layout)
+  const unsigned char *far_base = reinterpret_cast<const unsigned char *>(
+      S.ref + (lane / FarL<T, W, SKIP>::NW) * FarL<T, W, SKIP>::RSTEP * S.stride) + 4 * (lane % FarL<T, W, SKIP>::NW);
   start.col = iclamp(start.col, S.lim.col_min, S.lim.col_max);
   start.row = iclamp(start.row, S.lim.row_min, S.lim.row_max);
   const int tot_steps = 15 - search_step;
@@ -537,32 +568,31 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
       }
       mykey = group_min_u32<L::LPC>(mykey);
     } else {
-      // far stage: one candidate per warp pass, row-major lanes, 4 candidates in flight
+      // far stage: one candidate per warp pass, row-major lanes, 4 candidates in flight.
+      // Lane l < nsites prepares site l + 1 once (position, cost, validity, byte offset); the
+      // evaluation loop only broadcasts.
       const int mine = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // candidate this lane owns after reduce4
+      const int sidx = lane < nsites ? lane + 1 : 0;
+      const int sr = best.row + c_sites.r[step][sidx], sc = best.col + c_sites.c[step][sidx];
+      const unsigned scost = (unsigned)sad_cost(S, sr, sc);
+      // exact pruning: sad + cost < bestsad is impossible once cost >= bestsad
+      const bool sok = (lane < nsites) & (all_in | in_range(S.lim, sr, sc)) & (scost < bestsad);
+      const int soff = (sr * S.stride + sc) * (int)sizeof(T);
+      const unsigned okmask = __ballot_sync(FULL, sok);
+      ncand += __popc(okmask);
 #pragma unroll 1
-      for (int idx0 = 1; idx0 <= nsites; idx0 += 4) {
-        unsigned part[4], cst[4];
-        bool okv[4];
-        bool any_ok = false;
+      for (int i0 = 0; i0 < nsites; i0 += 4) {
+        if (((okmask >> i0) & 15u) == 0) continue;
+        unsigned part[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          const int cr = best.row + c_sites.r[step][idx0 + u], cc = best.col + c_sites.c[step][idx0 + u];
-          cst[u] = (unsigned)sad_cost(S, cr, cc);
-          // exact pruning: sad + cost < bestsad is impossible once cost >= bestsad
-          okv[u] = (all_in || in_range(S.lim, cr, cc)) && cst[u] < bestsad;
-          any_ok |= okv[u];
-          ncand += okv[u];
-          part[u] = okv[u] ? far_partial<T, W, SKIP>(S.ref, S.stride, cr, cc, lane, sf) : 0u;
+          const int off = __shfl_sync(FULL, soff, i0 + u);
+          part[u] = ((okmask >> (i0 + u)) & 1u) ? far_partial_off<T, W, SKIP>(far_base, off, S.stride, sf) : 0u;
         }
-        if (!any_ok) continue;
         const unsigned tot4 = reduce4_u32(part, lane);
-        // this lane owns candidate `mine` (0..3): pick its cost / validity from the uniform values
-        const unsigned c01 = (mine & 1) ? cst[1] : cst[0], c23 = (mine & 1) ? cst[3] : cst[2];
-        const bool o01 = (mine & 1) ? okv[1] : okv[0], o23 = (mine & 1) ? okv[3] : okv[2];
-        const unsigned my_cost = (mine & 2) ? c23 : c01;
-        const bool my_ok = (mine & 2) ? o23 : o01;
+        const unsigned my_cost = __shfl_sync(FULL, scost, i0 + mine);
         const unsigned tot = sad_post<SKIP>(tot4, S.hbd_shift) + my_cost;
-        mykey = min(mykey, my_ok ? ((tot << 4) | (unsigned)(idx0 + mine)) : 0xffffffffu);
+        mykey = min(mykey, ((okmask >> (i0 + mine)) & 1u) ? ((tot << 4) | (unsigned)(i0 + mine + 1)) : 0xffffffffu);
       }
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 8));
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 16));
