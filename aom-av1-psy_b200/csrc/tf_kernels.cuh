@@ -113,6 +113,15 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
   return v;
 }
 
+// Warp sum of a per-lane (sum, sse) pair with one 64-bit reduction: |sum| <= 32 * 4095 < 2^17 per
+// lane, so sum + 2^17 is non-negative and the 32-lane total stays below 2^23; sse totals < 2^35.
+__device__ __forceinline__ unsigned long long warp_sum_pair(int &sum, unsigned sse) {
+  unsigned long long v = ((unsigned long long)sse << 24) | (unsigned)(sum + (1 << 17));
+  v = warp_sum_u64(v);
+  sum = (int)(v & 0xffffffu) - (1 << 22);
+  return v >> 24;
+}
+
 // ---------------------------------------------------------------------------
 // Search context (warp-uniform)
 // ---------------------------------------------------------------------------
@@ -479,8 +488,7 @@ __device__ __noinline__ unsigned variance(const T *a, int as, const T *b, int bs
     sum += d;
     sse += (unsigned)(d * d);
   }
-  sum = warp_sum_i32(sum);
-  const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
+  const unsigned long long sse64 = warp_sum_pair(sum, sse);
   return var_finish(sum, sse64, W, hbd_shift, sse_out);
 }
 
@@ -873,8 +881,7 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
     }
   }
   if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(W * W));
-  sum = warp_sum_i32(sum);
-  const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
+  const unsigned long long sse64 = warp_sum_pair(sum, sse);
   unsigned sse_out;
   return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
 }
@@ -936,8 +943,7 @@ __device__ __noinline__ unsigned upsampled_err(const Search<T> &S, int r8, int c
   }
   __syncwarp();
   if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(W * W));
-  sum = warp_sum_i32(sum);
-  const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
+  const unsigned long long sse64 = warp_sum_pair(sum, sse);
   unsigned sse_out;
   return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
 }
