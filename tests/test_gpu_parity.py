@@ -33,6 +33,13 @@ CASES = [
     ("i444_12_speed0", 72, 40, 3, 12, {}, dict(ss_x=0, ss_y=0, speed=0)),
     ("hd720_8_noskip_speed2", 736, 720, 2, 8, dict(motion=(1, 3)), dict(speed=2, use_downsampled_sad=0)),
     ("long_window_21", 96, 64, 21, 8, dict(motion=(0, 1)), dict(filter_frame_idx=10)),
+    ("speed4_hp_8", 176, 144, 3, 8, dict(motion=(1, 3)), dict(allow_hp=1)),
+    ("speed4_hp_10", 176, 144, 3, 10, dict(motion=(2, 1)), dict(allow_hp=1)),
+    ("speed1_tree_iters2_8", 176, 144, 3, 8, dict(motion=(2, 3)), dict(speed=1)),
+    ("pruned_iters2_hp", 176, 144, 3, 8, dict(motion=(1, 2)), dict(speed=3, subpel_iters_per_step=2, allow_hp=1)),
+    ("pruned_more_iters2_10", 176, 144, 3, 10, dict(motion=(3, 1)), dict(subpel_iters_per_step=2)),
+    ("strength0_q5", 128, 96, 3, 8, {}, dict(filter_strength=0, q_factor=5)),
+    ("strength6_q255", 128, 96, 3, 10, {}, dict(filter_strength=6, q_factor=255)),
 ]
 
 

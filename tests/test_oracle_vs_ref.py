@@ -29,6 +29,15 @@ CASES = [
     ("extreme", 96, 64, 3, 8, "r", dict(extreme=0), {}),
     ("hd_skip", 1280, 720, 2, 8, "m", {}, {}),
     ("hd_skip_rand_kf", 1280, 720, 2, 8, "r", {}, dict(filter_frame_idx=0)),
+    ("speed4_hp_8", 176, 144, 3, 8, "m", dict(motion=(1, 3)), dict(allow_hp=1)),
+    ("speed4_hp_10", 176, 144, 3, 10, "m", dict(motion=(2, 1)), dict(allow_hp=1)),
+    ("speed1_tree_iters2_8", 176, 144, 3, 8, "m", dict(motion=(2, 3)), dict(speed=1)),
+    ("pruned_iters2_hp", 176, 144, 3, 8, "m", dict(motion=(1, 2)), dict(speed=3, subpel_iters_per_step=2, allow_hp=1)),
+    ("pruned_more_iters2_10", 176, 144, 3, 10, "m", dict(motion=(3, 1)), dict(subpel_iters_per_step=2)),
+    ("strength0_q5", 128, 96, 3, 8, "m", {}, dict(filter_strength=0, q_factor=5)),
+    ("strength6_q255", 128, 96, 3, 10, "m", {}, dict(filter_strength=6, q_factor=255)),
+    ("long_window_21", 96, 64, 21, 8, "m", dict(motion=(0, 1)), dict(filter_frame_idx=10)),
+    ("tiny_17x33_10", 17, 33, 3, 10, "m", {}, dict(speed=1)),
 ]
 
 
