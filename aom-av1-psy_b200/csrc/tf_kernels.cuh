@@ -638,6 +638,8 @@ __device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param,
   const int further_steps = 15 - 1 - step_param;
   // first pass (pass_n = 0) and the refinement passes share one call site
   bool first = true;
+  MV2 memo_mv = { 0x7fff, 0x7fff };
+  int memo_sme = 0;
   while (first || n < further_steps) {
     if (!first) {
       ++n;
@@ -649,7 +651,16 @@ __device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param,
     MV2 tmp;
     int nn;
     int thissme = (int)diamond_search<T, W, SKIP>(S, start, step_param + (first ? 0 : n), &nn, &tmp);
-    if (thissme < INT_MAX_) thissme = var_cost<T, W>(S, tmp.row, tmp.col);
+    if (thissme < INT_MAX_) {
+      // var_cost is a pure function of the MV: passes that end on an MV already scored reuse the value
+      if (!first && tmp.row == best_mv->row && tmp.col == best_mv->col) thissme = bestsme;
+      else if (!first && tmp.row == memo_mv.row && tmp.col == memo_mv.col) thissme = memo_sme;
+      else {
+        thissme = var_cost<T, W>(S, tmp.row, tmp.col);
+        memo_mv = tmp;
+        memo_sme = thissme;
+      }
+    }
     if (first) {
       n = nn;
       bestsme = thissme;
