@@ -128,25 +128,47 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # CPU arm
 # ---------------------------------------------------------------------------------------
-def cpu_filter_class():
+SIMD_NOTE = ("avx2: SAD/variance/sub-pel variance/12-tap convolve/apply_temporal_filter bound to the reference's "
+             "AVX2 intrinsics (oracle/_ref/libtf_ref_avx2.so; aom_sad16x16 single-ref stays C, its only SIMD is asm)")
+
+
+def cpu_filter_class(simd="auto"):
+    """(factory, kind, simd) -- the compiled reference when it travelled with the repo, else the
+    oracle port.  simd: "auto" picks the AVX2-bound flavour when the host has AVX2."""
+    import functools
     import _ref
     if _ref.available():
-        return _ref.RefFilter, "reference"
+        if simd in ("auto", "avx2") and _ref.avx2_available():
+            return functools.partial(_ref.RefFilter, avx2=True), "reference", "avx2"
+        return _ref.RefFilter, "reference", "none (generic C)"
     import _oracle
-    return _oracle.OracleFilter, "port"
+    return _oracle.OracleFilter, "port", "none (scalar C port)"
 
 
-def cpu_baseline(p, frames, rows, mb_rows):
-    """1-core bounded sample: block rows `rows` of the window."""
-    cls, kind = cpu_filter_class()
+def _time_rows(cls, p, frames, rows):
     f = cls(p, frames)
     t = time.perf_counter()
     f.run(record=False, rows=rows)
     dt = time.perf_counter() - t
     f.close()
+    return dt
+
+
+def cpu_baseline(p, frames, rows, mb_rows, simd="auto"):
+    """1-core bounded sample: block rows `rows` of the window.  The headline value is the fastest
+    faithful reference build available (AVX2-bound when the host has it); the generic-C figure of
+    the same sample is reported beside it."""
+    cls, kind, used = cpu_filter_class(simd)
+    dt = _time_rows(cls, p, frames, rows)
     frac = (rows[1] - rows[0]) / mb_rows
-    return {"value": frac / dt, "unit": "frames/s", "cores": 1, "kind": kind,
-            "sample": f"block rows [{rows[0]},{rows[1]}) of {mb_rows} of one window ({dt:.2f} s)"}
+    out = {"value": frac / dt, "unit": "frames/s", "cores": 1, "kind": kind, "simd": used,
+           "sample": f"block rows [{rows[0]},{rows[1]}) of {mb_rows} of one window ({dt:.2f} s)"}
+    if used == "avx2":
+        out["simd_note"] = SIMD_NOTE
+        cls_c, _, _ = cpu_filter_class("c")
+        dt_c = _time_rows(cls_c, p, frames, rows)
+        out["generic_c"] = {"value": frac / dt_c, "unit": "frames/s", "cores": 1, "sample_s": round(dt_c, 2)}
+    return out
 
 
 def _ref_worker(conn, filt):
@@ -170,7 +192,7 @@ def run_reference_arm(args, wl):
     width, height, bd, n, strength = WORKLOADS[wl]
     frames = make_window(width, height, bd, n, seed=77 if bd > 8 else 1234)
     p = _params.tf_params(width, height, n, bit_depth=bd, q_factor=Q_FACTOR, filter_strength=strength)
-    cls, kind = cpu_filter_class()
+    cls, kind, simd = cpu_filter_class(args.ref_simd)
     filt = cls(p, frames)
     p["noise_levels"] = tuple(filt.estimate_noise())
     filt.close()
@@ -220,7 +242,8 @@ def run_reference_arm(args, wl):
         "dtype": "u16" if bd > 8 else "u8", "data": "synthetic",
         "config": {"workload": wl, "width": width, "height": height, "bit_depth": bd, "num_frames": n,
                    "speed_class": "good cpu-used=4", "note": "ms_per_step is per whole frame (sample time / sampled fraction)"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": nw, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": nw, "kind": kind, "simd": simd,
+                         "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -239,6 +262,8 @@ def main():
     ap.add_argument("--mode", default="windows", choices=["windows", "slab"])
     ap.add_argument("--impl", default="tfgpu", choices=["tfgpu", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-simd", default="auto", choices=["auto", "avx2", "c"],
+                    help="CPU reference flavour: auto = AVX2-bound build when the host has AVX2, c = generic C")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--concurrent", type=int, default=0,
                     help="independent windows in flight per GPU (contexts); 0 = auto: 2 for 4K, 4 below")
@@ -518,11 +543,11 @@ def main():
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:
         mid = mb_rows // 2
-        nrows = 4 if width >= 3000 else (8 if width >= 1900 else mb_rows)
+        nrows = 12 if width >= 3000 else (24 if width >= 1900 else mb_rows)
         rows = (max(0, mid - nrows // 2), min(mb_rows, mid - nrows // 2 + nrows))
         pc = dict(p)
         pc["out_row_begin"] = pc["out_row_end"] = 0
-        line["cpu_baseline"] = cpu_baseline(pc, windows[0][0], rows, mb_rows)
+        line["cpu_baseline"] = cpu_baseline(pc, windows[0][0], rows, mb_rows, args.ref_simd)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -56,6 +56,14 @@ static void tfref_apply_hook(const YV12_BUFFER_CONFIG *frame_to_filter,
                              const uint8_t *pred, uint32_t *accum,
                              uint16_t *count);
 
+/* whatever the rtcd header bound these names to (_c, or _avx2 in the libtf_ref_avx2.so flavour) */
+typedef void (*tfref_apply_fn)(const YV12_BUFFER_CONFIG *, const MACROBLOCKD *, const BLOCK_SIZE,
+                               const int, const int, const int, const double *, const MV *,
+                               const int *, const int, const int, const uint8_t *, uint32_t *,
+                               uint16_t *);
+static const tfref_apply_fn tfref_apply_lbd = av1_apply_temporal_filter;
+static const tfref_apply_fn tfref_apply_hbd = av1_highbd_apply_temporal_filter;
+
 #undef av1_apply_temporal_filter
 #define av1_apply_temporal_filter tfref_apply_hook
 #undef av1_highbd_apply_temporal_filter
@@ -97,10 +105,9 @@ static void tfref_apply_hook(const YV12_BUFFER_CONFIG *frame_to_filter,
       }
     }
   }
-  av1_apply_temporal_filter_c(frame_to_filter, mbd, block_size, mb_row, mb_col,
-                              num_planes, noise_levels, subblock_mvs,
-                              subblock_mses, q_factor, filter_strength, pred,
-                              accum, count);
+  ((frame_to_filter->flags & YV12_FLAG_HIGHBITDEPTH) ? tfref_apply_hbd : tfref_apply_lbd)(
+      frame_to_filter, mbd, block_size, mb_row, mb_col, num_planes, noise_levels, subblock_mvs,
+      subblock_mses, q_factor, filter_strength, pred, accum, count);
 }
 
 /* ---- symbols the dropped control-plane would have provided -------------- */

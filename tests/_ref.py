@@ -26,6 +26,26 @@ class RefCfg(C.Structure):
         ("use_downsampled_sad", C.c_int),
         ("compute_frame_diff", C.c_int),
     ]
+# same harness with the hot-path rtcd names bound to the reference's AVX2 intrinsics (CPU timing baseline)
+AVX2_LIB = os.path.join(HERE, "..", "oracle", "_ref", "libtf_ref_avx2.so")
+
+
+def avx2_available():
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+    return os.path.exists(AVX2_LIB) and " avx2" in flags
+
+
+_avx2 = None
+
+
+def avx2_lib():
+    global _avx2
+    if _avx2 is None:
+        _avx2 = _bind(C.CDLL(AVX2_LIB))
+    return _avx2
 
 
 def available():
@@ -100,10 +120,10 @@ def make_cfg(p):
 
 
 class RefFilter:
-    def __init__(self, p, frames, seam=False):
+    def __init__(self, p, frames, seam=False, avx2=False):
         self.p = dict(p)
         self.cfg = make_cfg(p)
-        self.L = seam_lib() if seam else lib()
+        self.L = seam_lib() if seam else avx2_lib() if avx2 else lib()
         self.h = self.L.tfref_create(C.byref(self.cfg))
         assert self.h
         self.num_planes = 1 if p["monochrome"] else 3
