@@ -147,7 +147,7 @@ struct Search {
   unsigned long long *ctr;
 };
 
-constexpr int WIN_BYTES = 12288;  // window capacity per warp, 32x32 search
+constexpr int WIN_BYTES = 9472;  // window capacity per warp, 32x32 search
 constexpr int WIN16_BYTES = 4608;  // 16x16 search (R = 12): lets >= 24 warps share an SM
 
 // SAD lane layout: a candidate occupies LPC lanes (one block row per lane, every
@@ -1165,7 +1165,7 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
 // Kernel 1: the 32x32 search of every frame of the window, chained through
 // ref_mv (temporal_filter.c:855-871).  One warp per 32x32 block.
 template <typename T>
-__global__ void __launch_bounds__(32, 16) tf_search32_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(32, 20) tf_search32_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id();
   const int mb_row = P.row_begin + blockIdx.x / P.mb_cols;
