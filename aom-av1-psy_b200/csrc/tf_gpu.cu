@@ -462,8 +462,8 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     }
     if (timed) cudaEventRecord(ctx->evk[1], ctx->stream);
   }
-  if (g.is_hbd) tf_filter_kernel<uint16_t><<<grid, 32, smem_filter, ctx->stream>>>(K);
-  else tf_filter_kernel<uint8_t><<<grid, 32, smem_filter, ctx->stream>>>(K);
+  if (g.is_hbd) tf_filter_kernel<uint16_t><<<grid, FILT_THREADS, smem_filter, ctx->stream>>>(K);
+  else tf_filter_kernel<uint8_t><<<grid, FILT_THREADS, smem_filter, ctx->stream>>>(K);
   nlaunch++;
   CU(cudaGetLastError());
   if (timed) CU(cudaEventRecord(ctx->ev1, ctx->stream));

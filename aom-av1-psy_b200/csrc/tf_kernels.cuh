@@ -1328,9 +1328,16 @@ __device__ __noinline__ void convolve12(const KParams &P, const T *src, int ss, 
   }
 }
 
+// The filter kernel runs FILT_WARPS = 4 warps per 32x32 block: warp q builds the predictor of
+// sub-block q of every plane (its own MV), the element-wise stages stride over all threads.
+constexpr int FILT_WARPS = 4;
+constexpr int FILT_THREADS = FILT_WARPS * 32;
+
 template <typename T>
 __device__ void build_predictor(const KParams &P, const T *const ref[3], int mb_row, int mb_col, const MV2 *mvs,
-                                T *pred, int16_t *im) {
+                                T *pred, int16_t *im /* this warp's scratch */) {
+  const int q = threadIdx.x >> 5;  // sub-block of this warp, raster order (temporal_filter.c:366-385)
+  const MV2 mv = mvs[q];
   int plane_offset = 0;
   for (int plane = 0; plane < P.num_planes; plane++) {
     const int ssy = plane ? P.ss_y : 0, ssx = plane ? P.ss_x : 0;
@@ -1338,24 +1345,19 @@ __device__ void build_predictor(const KParams &P, const T *const ref[3], int mb_
     const int plane_h = 32 >> ssy, plane_w = 32 >> ssx;
     const int plane_y = (32 * mb_row) >> ssy, plane_x = (32 * mb_col) >> ssx;
     const int h = plane_h >> 1, w = plane_w >> 1;
-    int idx = 0;
-    for (int i = 0; i < plane_h; i += h) {
-      for (int j = 0; j < plane_w; j += w) {
-        const MV2 mv = mvs[idx++];
-        const int y = plane_y + i, x = plane_x + j;
-        int pos_y = ((y << 4) + mv.row * (1 << (1 - ssy))) * 64 + 32;
-        int pos_x = ((x << 4) + mv.col * (1 << (1 - ssx))) * 64 + 32;
-        const int top = -(((288 >> ssy) - 4) << 10), left = -(((288 >> ssx) - 4) << 10);
-        pos_y = iclamp(pos_y, top, (P.aligned_h[k] + 4) << 10);
-        pos_x = iclamp(pos_x, left, (P.aligned_w[k] + 4) << 10);
-        const T *src = ref[plane] + (pos_y >> 10) * P.pitch[k] + (pos_x >> 10);
-        convolve12<T>(P, src, P.pitch[k], &pred[plane_offset + i * plane_w + j], plane_w, w, h, (pos_x & 1023) >> 6,
-                      (pos_y & 1023) >> 6, im);
-      }
-    }
+    const int i = (q >> 1) * h, j = (q & 1) * w;
+    const int y = plane_y + i, x = plane_x + j;
+    int pos_y = ((y << 4) + mv.row * (1 << (1 - ssy))) * 64 + 32;
+    int pos_x = ((x << 4) + mv.col * (1 << (1 - ssx))) * 64 + 32;
+    const int top = -(((288 >> ssy) - 4) << 10), left = -(((288 >> ssx) - 4) << 10);
+    pos_y = iclamp(pos_y, top, (P.aligned_h[k] + 4) << 10);
+    pos_x = iclamp(pos_x, left, (P.aligned_w[k] + 4) << 10);
+    const T *src = ref[plane] + (pos_y >> 10) * P.pitch[k] + (pos_x >> 10);
+    convolve12<T>(P, src, P.pitch[k], &pred[plane_offset + i * plane_w + j], plane_w, w, h, (pos_x & 1023) >> 6,
+                  (pos_y & 1023) >> 6, im);
     plane_offset += plane_h * plane_w;
   }
-  __syncwarp();
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
@@ -1367,7 +1369,8 @@ template <typename T>
 __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row, int mb_col, const MV2 *mvs,
                              const int *mses, const T *pred, uint32_t *accum, uint16_t *count, uint32_t *sq,
                              uint32_t *lsum) {
-  const int lane = lane_id();
+  constexpr int NT = FILT_THREADS;
+  const int tid = threadIdx.x;
   const double inv_factor = 1.0 / ((5 + 1) * 20);
   const double weight_factor = (double)5 * inv_factor;
   double d_factor[4];
@@ -1380,50 +1383,58 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
   int plane_offset = 0;
   for (int plane = 0; plane < P.num_planes; plane++) {
     const int ssy = plane ? P.ss_y : 0, ssx = plane ? P.ss_x : 0;
-    const int h = 32 >> ssy, w = 32 >> ssx;
+    const int h = 32 >> ssy, w = 32 >> ssx, n = h * w;
     const int st = P.pitch[plane > 0];
     const T *src = cur[plane] + mb_row * h * st + mb_col * w;
     const int num_ref_pixels = 25 + (plane ? (1 << (ssx + ssy)) : 0);
     const double inv_num_ref_pixels = 1.0 / num_ref_pixels;
-    if (plane == 1) {  // compute_luma_sq_error_sum (:507-522); sq still holds the raw luma squares
-      for (int idx = lane; idx < h * w; idx += 32) {
+    if (plane == 1) {  // compute_luma_sq_error_sum (:507-522); lsum still holds the raw luma squares
+      for (int idx = tid; idx < n; idx += NT) {
         const int i = idx / w, j = idx - i * w;
         uint32_t s = 0;
         for (int ii = 0; ii < (1 << ssy); ii++)
           for (int jj = 0; jj < (1 << ssx); jj++) s += lsum[((i << ssy) + ii) * 32 + (j << ssx) + jj];
         sq[idx] = s;  // staged in sq, copied back below
       }
-      __syncwarp();
-      for (int idx = lane; idx < h * w; idx += 32) lsum[idx] = sq[idx];
-      __syncwarp();
+      __syncthreads();
+      for (int idx = tid; idx < n; idx += NT) lsum[idx] = sq[idx];
+      __syncthreads();
     }
     // compute_square_diff (:463-493)
-    for (int idx = lane; idx < h * w; idx += 32) {
+    for (int idx = tid; idx < n; idx += NT) {
       const int i = idx / w, j = idx - i * w;
       const int d = (int)__ldg(src + i * st + j) - (int)pred[plane_offset + idx];
-      sq[idx] = (uint32_t)(d * d);
+      const uint32_t v = (uint32_t)(d * d);
+      sq[idx] = v;
+      if (plane == 0 && P.num_planes > 1) lsum[idx] = v;
     }
-    __syncwarp();
-    if (plane == 0 && P.num_planes > 1) {
-      for (int idx = lane; idx < 1024; idx += 32) lsum[idx] = sq[idx];
-      __syncwarp();
-    }
-    // horizontal 5-sums with edge clamp, in place (each lane owns whole rows of its column set)
+    __syncthreads();
+    // horizontal 5-sums with edge clamp, in place: every thread reads its samples' neighbourhoods
+    // first, the block synchronises, then the sums replace the squares
     {
-      const int rp = 32 / w, col = lane % w, rr = lane / w;
-      for (int i = rr; i < h; i += rp) {
-        uint32_t s = 0;
+      uint32_t hs[1024 / NT];
 #pragma unroll
-        for (int dj = -2; dj <= 2; dj++) s += sq[i * w + iclamp(col + dj, 0, w - 1)];
-        __syncwarp();
-        sq[i * w + col] = s;
-        __syncwarp();
+      for (int k = 0; k < 1024 / NT; k++) {
+        const int idx = tid + k * NT;
+        hs[k] = 0;
+        if (idx < n) {
+          const int i = idx / w, col = idx - i * w;
+#pragma unroll
+          for (int dj = -2; dj <= 2; dj++) hs[k] += sq[i * w + iclamp(col + dj, 0, w - 1)];
+        }
       }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 1024 / NT; k++) {
+        const int idx = tid + k * NT;
+        if (idx < n) sq[idx] = hs[k];
+      }
+      __syncthreads();
     }
-    __syncwarp();
-    for (int idx = lane; idx < h * w; idx += 32) {
+    for (int idx = tid; idx < n; idx += NT) {
       const int i = idx / w, j = idx - i * w;
-      unsigned long long sum_square_diff = 0;
+      // 25 (+4) squares of at most 4095^2: fits 32 bits
+      uint32_t sum_square_diff = 0;
 #pragma unroll
       for (int di = -2; di <= 2; di++) sum_square_diff += sq[iclamp(i + di, 0, h - 1) * w + j];
       if (plane) sum_square_diff += lsum[idx];
@@ -1440,8 +1451,8 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
       accum[pidx] += (uint32_t)(weight * (int)pred[pidx]);
       count[pidx] = (uint16_t)(count[pidx] + weight);
     }
-    __syncwarp();
-    plane_offset += h * w;
+    __syncthreads();
+    plane_offset += n;
   }
 }
 
@@ -1450,22 +1461,25 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
 // predictor, weights, accumulate; then normalise and FRAME_DIFF
 // (av1_tf_do_filtering_row, temporal_filter.c:857-937).  accum / count / pred
 // never leave shared memory.
-// Warp-private shared memory, carved at run time (num_pels = 1024 luma + chroma:
+// Block-private shared memory, carved at run time (num_pels = 1024 luma + chroma:
 // 1536 for 4:2:0, 2048 for 4:2:2, 3072 for 4:4:4):
 //   accum u32[num_pels] | sq u32[1024] | lsum u32[1024] | count u16[num_pels] |
-//   pred (T view of u16[num_pels]) | im i16[27*16]
+//   pred (T view of u16[num_pels]) | im i16[FILT_WARPS][27*16] | red u64[FILT_WARPS]
 // ---------------------------------------------------------------------------
 struct WarpSmem {
   uint32_t *accum, *sq, *lsum;
   uint16_t *count, *pred;
   int16_t *im;
+  unsigned long long *red;
 };
+constexpr int FILT_IM = (16 + 11) * 16;  // intermediate rows of one 2-D 12-tap sub-block
 __host__ __device__ inline size_t filter_smem_bytes(int num_pels) {
-  return (size_t)num_pels * 8 + 2 * 1024 * 4 + (16 + 11) * 16 * 2;
+  return (size_t)num_pels * 8 + 2 * 1024 * 4 + FILT_WARPS * FILT_IM * 2 + FILT_WARPS * 8;
 }
 __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels) {
   WarpSmem sm;
-  sm.accum = reinterpret_cast<uint32_t *>(raw);
+  sm.red = reinterpret_cast<unsigned long long *>(raw);
+  sm.accum = reinterpret_cast<uint32_t *>(sm.red + FILT_WARPS);
   sm.sq = sm.accum + num_pels;
   sm.lsum = sm.sq + 1024;
   sm.count = reinterpret_cast<uint16_t *>(sm.lsum + 1024);
@@ -1475,20 +1489,21 @@ __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels)
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32) tf_filter_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(FILT_THREADS, 6) tf_filter_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = FILT_THREADS;
   const WarpSmem sm = carve_smem(smem_raw, P.num_pels);
-  const int lane = lane_id();
+  const int tid = threadIdx.x;
   const int mb_row = P.row_begin + blockIdx.x / P.mb_cols;
   const int mb_col = blockIdx.x % P.mb_cols;
   const int blk = mb_row * P.mb_cols + mb_col;
   T *pred = reinterpret_cast<T *>(sm.pred);
 
-  for (int i = lane; i < P.num_pels; i += 32) {
+  for (int i = tid; i < P.num_pels; i += NT) {
     sm.accum[i] = 0;
     sm.count[i] = 0;
   }
-  __syncwarp();
+  __syncthreads();
 
   const T *cur[3];
   for (int pl = 0; pl < 3; pl++) cur[pl] = reinterpret_cast<const T *>(P.frm[P.filter_idx][pl]);
@@ -1500,14 +1515,14 @@ __global__ void __launch_bounds__(32) tf_filter_kernel(const __grid_constant__ K
       for (int pl = 0; pl < P.num_planes; pl++) {
         const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.pitch[pl > 0];
         const T *b = cur[pl] + mb_row * h * st + mb_col * w;
-        for (int idx = lane; idx < h * w; idx += 32) {
+        for (int idx = tid; idx < h * w; idx += NT) {
           const int i = idx / w, j = idx - i * w;
           sm.accum[off + idx] += 1000u * (uint32_t)__ldg(b + i * st + j);
           sm.count[off + idx] = (uint16_t)(sm.count[off + idx] + 1000);
         }
         off += h * w;
       }
-      __syncwarp();
+      __syncthreads();
       continue;
     }
     const T *ref[3];
@@ -1546,56 +1561,59 @@ __global__ void __launch_bounds__(32) tf_filter_kernel(const __grid_constant__ K
         }
       }
     }
-    build_predictor<T>(P, ref, mb_row, mb_col, sub_mvs, pred, sm.im);
-    if (P.d_mvs && lane == 0) {
+    build_predictor<T>(P, ref, mb_row, mb_col, sub_mvs, pred, sm.im + (tid >> 5) * FILT_IM);
+    if (P.d_mvs && tid == 0) {
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         P.d_mvs[(bf * 4 + i) * 2 + 0] = (int16_t)sub_mvs[i].row;
         P.d_mvs[(bf * 4 + i) * 2 + 1] = (int16_t)sub_mvs[i].col;
       }
     }
-    if (P.d_mses && lane == 0) {
+    if (P.d_mses && tid == 0) {
 #pragma unroll
       for (int i = 0; i < 4; i++) P.d_mses[bf * 4 + i] = sub_mses[i];
     }
     if (P.d_pred)
-      for (int i = lane; i < P.num_pels; i += 32) P.d_pred[bf * P.num_pels + i] = (uint16_t)pred[i];
+      for (int i = tid; i < P.num_pels; i += NT) P.d_pred[bf * P.num_pels + i] = (uint16_t)pred[i];
     apply_filter<T>(P, cur, mb_row, mb_col, sub_mvs, sub_mses, pred, sm.accum, sm.count, sm.sq, sm.lsum);
   }
 
   // tf_normalize_filtered_frame (:740-777); OD_DIVU == integer division here
   // (proved exhaustively against the reference for count in [1000,1023]).
+  // FRAME_DIFF (:921-937): vf(src, out, &sse) on the 32x32 luma block, fused into the luma pass.
+  unsigned sse = 0;
   {
     int off = 0;
     for (int pl = 0; pl < P.num_planes; pl++) {
       const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.out_pitch[pl > 0];
       T *o = reinterpret_cast<T *>(P.out[pl]) + mb_row * h * st + mb_col * w;
-      for (int idx = lane; idx < h * w; idx += 32) {
+      const T *a = cur[pl] + mb_row * h * P.pitch[pl > 0] + mb_col * w;
+      for (int idx = tid; idx < h * w; idx += NT) {
         const int i = idx / w, j = idx - i * w;
         const uint32_t c = sm.count[off + idx];
         const uint32_t v = (sm.accum[off + idx] + (c >> 1)) / c;
         o[i * st + j] = (T)v;
-        if (pl == 0) sm.sq[idx] = v;  // keep the filtered luma for FRAME_DIFF
+        if (pl == 0 && P.compute_diff) {
+          const int d = (int)__ldg(a + i * P.pitch[0] + j) - (int)v;
+          sse += (unsigned)(d * d);
+        }
       }
       off += h * w;
     }
-    __syncwarp();
   }
   if (P.d_accum)
-    for (int i = lane; i < P.num_pels; i += 32) P.d_accum[(size_t)blk * P.num_pels + i] = sm.accum[i];
+    for (int i = tid; i < P.num_pels; i += NT) P.d_accum[(size_t)blk * P.num_pels + i] = sm.accum[i];
   if (P.d_count)
-    for (int i = lane; i < P.num_pels; i += 32) P.d_count[(size_t)blk * P.num_pels + i] = sm.count[i];
+    for (int i = tid; i < P.num_pels; i += NT) P.d_count[(size_t)blk * P.num_pels + i] = sm.count[i];
 
-  if (P.compute_diff) {  // :921-937: vf(src, out, &sse) on the 32x32 luma block
-    const int st = P.pitch[0];
-    const T *a = cur[0] + mb_row * 32 * st + mb_col * 32;
-    unsigned sse = 0;
-    for (int i = 0; i < 32; i++) {
-      const int d = (int)__ldg(a + i * st + lane) - (int)sm.sq[i * 32 + lane];
-      sse += (unsigned)(d * d);
-    }
-    const unsigned long long sse64 = warp_sum_u64((unsigned long long)sse);
-    if (lane == 0) {
+  if (P.compute_diff) {
+    const unsigned long long w64 = warp_sum_u64((unsigned long long)sse);
+    if ((tid & 31) == 0) sm.red[tid >> 5] = w64;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long sse64 = 0;
+#pragma unroll
+      for (int q = 0; q < FILT_WARPS; q++) sse64 += sm.red[q];
       unsigned sse32;
       if (P.hbd_shift == 0) sse32 = (unsigned)sse64;
       else sse32 = (unsigned)((sse64 + ((1ull << (2 * P.hbd_shift)) >> 1)) >> (2 * P.hbd_shift));
