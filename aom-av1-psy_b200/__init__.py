@@ -16,6 +16,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtf_gpu.so")
+# development only: point at another build of the same library (A/B runs of two kernels on one box)
+LIB_PATH = os.environ.get("TF_GPU_LIB", LIB_PATH)
 
 TF_GPU_MAX_FRAMES = 24
 NOISE_ESTIMATION_EDGE_THRESHOLD = 50  # temporal_filter.h:79

@@ -1383,14 +1383,14 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
   int plane_offset = 0;
   for (int plane = 0; plane < P.num_planes; plane++) {
     const int ssy = plane ? P.ss_y : 0, ssx = plane ? P.ss_x : 0;
-    const int h = 32 >> ssy, w = 32 >> ssx, n = h * w;
+    const int h = 32 >> ssy, w = 32 >> ssx, n = h * w, wsh = 5 - ssx;
     const int st = P.pitch[plane > 0];
     const T *src = cur[plane] + mb_row * h * st + mb_col * w;
     const int num_ref_pixels = 25 + (plane ? (1 << (ssx + ssy)) : 0);
     const double inv_num_ref_pixels = 1.0 / num_ref_pixels;
     if (plane == 1) {  // compute_luma_sq_error_sum (:507-522); lsum still holds the raw luma squares
       for (int idx = tid; idx < n; idx += NT) {
-        const int i = idx / w, j = idx - i * w;
+        const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
         uint32_t s = 0;
         for (int ii = 0; ii < (1 << ssy); ii++)
           for (int jj = 0; jj < (1 << ssx); jj++) s += lsum[((i << ssy) + ii) * 32 + (j << ssx) + jj];
@@ -1402,7 +1402,7 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
     }
     // compute_square_diff (:463-493)
     for (int idx = tid; idx < n; idx += NT) {
-      const int i = idx / w, j = idx - i * w;
+      const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
       const int d = (int)__ldg(src + i * st + j) - (int)pred[plane_offset + idx];
       const uint32_t v = (uint32_t)(d * d);
       sq[idx] = v;
@@ -1418,7 +1418,7 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
         const int idx = tid + k * NT;
         hs[k] = 0;
         if (idx < n) {
-          const int i = idx / w, col = idx - i * w;
+          const int i = idx >> wsh, col = idx & (w - 1);
 #pragma unroll
           for (int dj = -2; dj <= 2; dj++) hs[k] += sq[i * w + iclamp(col + dj, 0, w - 1)];
         }
@@ -1432,7 +1432,7 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
       __syncthreads();
     }
     for (int idx = tid; idx < n; idx += NT) {
-      const int i = idx / w, j = idx - i * w;
+      const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
       // 25 (+4) squares of at most 4095^2: fits 32 bits
       uint32_t sum_square_diff = 0;
 #pragma unroll
@@ -1514,9 +1514,10 @@ __global__ void __launch_bounds__(FILT_THREADS, 6) tf_filter_kernel(const __grid
       int off = 0;
       for (int pl = 0; pl < P.num_planes; pl++) {
         const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.pitch[pl > 0];
+        const int wsh = 5 - (pl ? P.ss_x : 0);
         const T *b = cur[pl] + mb_row * h * st + mb_col * w;
         for (int idx = tid; idx < h * w; idx += NT) {
-          const int i = idx / w, j = idx - i * w;
+          const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
           sm.accum[off + idx] += 1000u * (uint32_t)__ldg(b + i * st + j);
           sm.count[off + idx] = (uint16_t)(sm.count[off + idx] + 1000);
         }
@@ -1586,10 +1587,11 @@ __global__ void __launch_bounds__(FILT_THREADS, 6) tf_filter_kernel(const __grid
     int off = 0;
     for (int pl = 0; pl < P.num_planes; pl++) {
       const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.out_pitch[pl > 0];
+      const int wsh = 5 - (pl ? P.ss_x : 0);
       T *o = reinterpret_cast<T *>(P.out[pl]) + mb_row * h * st + mb_col * w;
       const T *a = cur[pl] + mb_row * h * P.pitch[pl > 0] + mb_col * w;
       for (int idx = tid; idx < h * w; idx += NT) {
-        const int i = idx / w, j = idx - i * w;
+        const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
         const uint32_t c = sm.count[off + idx];
         const uint32_t v = (sm.accum[off + idx] + (c >> 1)) / c;
         o[i * st + j] = (T)v;
