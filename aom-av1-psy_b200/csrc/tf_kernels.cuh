@@ -546,6 +546,14 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
     const bool all_in = (best.row - rad >= S.lim.row_min) && (best.row + rad <= S.lim.row_max) &&
                         (best.col - rad >= S.lim.col_min) && (best.col + rad <= S.lim.col_max);
     unsigned mykey = 0xffffffffu;
+    // lane i holds the offset of site i of this stage (one constant load per stage; the per-pass
+    // lookups are shuffles instead of lane-divergent constant loads)
+    // (16x16 search only: the 32x32 search has two lane groups and no registers to spare)
+    constexpr bool SHFL_SITES = (W == 16);
+    const int site_r = (SHFL_SITES && lane <= nsites) ? (int)c_sites.r[step][lane] : 0;
+    const int site_c = (SHFL_SITES && lane <= nsites) ? (int)c_sites.c[step][lane] : 0;
+    auto site_row = [&](int i) { return SHFL_SITES ? __shfl_sync(FULL, site_r, i) : (int)c_sites.r[step][i]; };
+    auto site_col = [&](int i) { return SHFL_SITES ? __shfl_sync(FULL, site_c, i) : (int)c_sites.c[step][i]; };
     if (window_covers(S, best.row, best.col, rad)) {
       const unsigned worg = (unsigned)__cvta_generic_to_shared(S.win) +
                             (unsigned)((S.wR - S.wr) * S.wpitch + (S.wR - S.wc) * (int)sizeof(T) + S.wshift);
@@ -556,11 +564,12 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
         bool ok[PU];
 #pragma unroll
         for (int u = 0; u < PU; u++) {  // independent loads + partial SADs
+          if (u > 0 && (p0 + u) * L::CPP >= nsites) break;  // 8-site stages need fewer passes (uniform)
           const int idx = 1 + (p0 + u) * L::CPP + grp;
           const bool live = idx <= nsites;
           const int sidx = live ? idx : 0;  // site 0 = the centre: always inside the window
-          const int my_r = best.row + c_sites.r[step][sidx];
-          const int my_c = best.col + c_sites.c[step][sidx];
+          const int my_r = best.row + site_row(sidx);
+          const int my_c = best.col + site_col(sidx);
           cost[u] = sad_cost(S, my_r, my_c);
           // exact pruning: a site is accepted only if sad + cost < bestsad and sad >= 0
           ok[u] = live & (all_in | in_range(S.lim, my_r, my_c)) & ((unsigned)cost[u] < bestsad);
@@ -569,6 +578,7 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
         ncand += imin(PU * L::CPP, nsites - p0 * L::CPP);
 #pragma unroll
         for (int u = 0; u < PU; u++) {
+          if (u > 0 && (p0 + u) * L::CPP >= nsites) break;
           const unsigned tot = sad_post<SKIP>(seg_reduce_u32<L::LPC>(part[u]), S.hbd_shift) + (unsigned)cost[u];
           const unsigned key = (tot << 4) | (unsigned)(1 + (p0 + u) * L::CPP + grp);
           mykey = min(mykey, ok[u] ? key : 0xffffffffu);
@@ -581,7 +591,7 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
       // evaluation loop only broadcasts.
       const int mine = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);  // candidate this lane owns after reduce4
       const int sidx = lane < nsites ? lane + 1 : 0;
-      const int sr = best.row + c_sites.r[step][sidx], sc = best.col + c_sites.c[step][sidx];
+      const int sr = best.row + site_row(sidx), sc = best.col + site_col(sidx);
       const unsigned scost = (unsigned)sad_cost(S, sr, sc);
       // exact pruning: sad + cost < bestsad is impossible once cost >= bestsad
       const bool sok = (lane < nsites) & (all_in | in_range(S.lim, sr, sc)) & (scost < bestsad);
@@ -611,8 +621,8 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
       best_site = (int)(mykey & 15u);
     }
     if (best_site != 0) {
-      best.row += c_sites.r[step][best_site];
-      best.col += c_sites.c[step][best_site];
+      best.row += site_row(best_site);
+      best.col += site_col(best_site);
       is_off_center = 1;
     }
     if (is_off_center == 0) n00++;
