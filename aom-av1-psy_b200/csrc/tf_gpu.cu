@@ -58,6 +58,7 @@ struct Ticket {
 
 struct tf_gpu_ctx {
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // 16x16 searches overlap the 32x32 chain
   cudaStream_t copy_stream = nullptr;  // uploads overlap the search of earlier frames
@@ -438,8 +439,14 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
       Kf.frame_end = f + 1;
       if (f > 0 && f - 1 == p->filter_frame_idx) Kf.frame_begin = f - 1;  // negate ref_mv at the centre frame
       CU(cudaStreamWaitEvent(ctx->stream, frames[f]->ready, 0));  // uploads of later frames overlap this search
-      if (g.is_hbd) tf_search32_kernel<uint16_t><<<grid, 32, smem_search, ctx->stream>>>(Kf);
-      else tf_search32_kernel<uint8_t><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+      const bool one_wave = grid <= ctx->num_sms * S32_WARPS_HI;
+      if (g.is_hbd) {
+        if (one_wave) tf_search32_kernel<uint16_t, S32_WARPS_HI><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+        else tf_search32_kernel<uint16_t, S32_WARPS_LO><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+      } else {
+        if (one_wave) tf_search32_kernel<uint8_t, S32_WARPS_HI><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+        else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+      }
       nlaunch++;
       if (!p->force_integer_mv) {
         CU(cudaEventRecord(ctx->ev_f32[f], ctx->stream));
@@ -634,6 +641,10 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
     return TF_GPU_ERR_NO_DEVICE;
   }
   ctx->device = dev;
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) ctx->num_sms = sms;
+  }
   int slots = (cfg && cfg->max_cached_frames > 0) ? cfg->max_cached_frames : 32;
   if (slots < TF_GPU_MAX_FRAMES) slots = TF_GPU_MAX_FRAMES;
   ctx->cache.resize(slots);

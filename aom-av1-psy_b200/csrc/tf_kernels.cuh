@@ -1174,8 +1174,13 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
 
 // Kernel 1: the 32x32 search of every frame of the window, chained through
 // ref_mv (temporal_filter.c:855-871).  One warp per 32x32 block.
-template <typename T>
-__global__ void __launch_bounds__(32, 20) tf_search32_kernel(const __grid_constant__ KParams P) {
+// Two register budgets of the same code, chosen per launch by the host: MINB = 20 (96 registers,
+// 20 warps per SM) when the whole grid is resident at once (<= 148 * 20 blocks, e.g. 1080p), so
+// no second partial wave forms; MINB = 12 (168 registers, no spills) for larger grids, where the
+// latency-bound chain runs faster per launch and leaves registers for concurrent 16x16 launches.
+constexpr int S32_WARPS_HI = 20, S32_WARPS_LO = 12;
+template <typename T, int MINB>
+__global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id();
   const int mb_row = P.row_begin + blockIdx.x / P.mb_cols;
