@@ -147,6 +147,10 @@ struct Search {
   unsigned long long *ctr;
 };
 
+#ifndef TF_VAR_VIA_SUBPEL
+#define TF_VAR_VIA_SUBPEL 1
+#endif
+constexpr bool VAR_VIA_SUBPEL_ROUTINE = TF_VAR_VIA_SUBPEL != 0;
 constexpr int WIN_BYTES = 9472;  // window capacity per warp, 32x32 search
 constexpr int WIN16_BYTES = 4608;  // 16x16 search (R = 12): lets >= 24 warps share an SM
 
@@ -492,13 +496,23 @@ __device__ __noinline__ unsigned variance(const T *a, int as, const T *b, int bs
   return var_finish(sum, sse64, W, hbd_shift, sse_out);
 }
 
-// get_mvpred_var_cost (mcomp.c:645-664): vf(src, ref@mv) + L1 cost
+template <typename T, int W>
+__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int ctr_idx = 1);
+
+// get_mvpred_var_cost (mcomp.c:645-664): vf(src, ref@mv) + L1 cost.
+// For 16-bit samples the variance at a full-pel MV is the sub-pel error routine at phase (0, 0)
+// (both taps collapse to a copy): same packed arithmetic, and the reference block comes from the
+// shared-memory window whenever the MV lies inside it instead of from global memory.
 template <typename T, int W>
 __device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
-  unsigned sse;
-  const int v = (int)variance<T, W>(S.src, S.stride, S.ref + r * S.stride + c, S.stride, S.hbd_shift, &sse);
-  if (S.ctr && lane_id() == 0) atomicAdd(&S.ctr[2], (unsigned long long)(W * W));
-  return v + sse_cost(S, r * 8, c * 8);
+  if constexpr (sizeof(T) == 2 && VAR_VIA_SUBPEL_ROUTINE) {
+    return (int)bilinear_err<T, W>(S, r * 8, c * 8, 2) + sse_cost(S, r * 8, c * 8);
+  } else {
+    unsigned sse;
+    const int v = (int)variance<T, W>(S.src, S.stride, S.ref + r * S.stride + c, S.stride, S.hbd_shift, &sse);
+    if (S.ctr && lane_id() == 0) atomicAdd(&S.ctr[2], (unsigned long long)(W * W));
+    return v + sse_cost(S, r * 8, c * 8);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -863,7 +877,7 @@ __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2
 // aom_sub_pixel_variance (aom_dsp/variance.c:91-139,150-163; hbd :478-560):
 // 2-tap bilinear over (W+1) x (W+1) samples then variance(filtered, src).
 template <typename T, int W>
-__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8) {
+__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int ctr_idx) {
   const Search<T> S = S_in;
   const int lane = lane_id();
   const int fr = r8 >> 3, fc = c8 >> 3;
@@ -920,7 +934,7 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
         acch = __dp2a_hi(md, pb, acch);                                // sum d * (d >> 8)
       }
     }
-    if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(W * W));
+    if (S.ctr && lane == 0) atomicAdd(&S.ctr[ctr_idx], (unsigned long long)(W * W));
     int sum = (int)sumv - (int)sums;
     const unsigned long long sse64 = warp_sum_pair(sum, accl + (acch << 8));
     unsigned sse_out;
