@@ -497,7 +497,7 @@ __device__ __noinline__ unsigned variance(const T *a, int as, const T *b, int bs
 }
 
 template <typename T, int W>
-__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int ctr_idx = 1);
+__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int mode = 1);
 
 // get_mvpred_var_cost (mcomp.c:645-664): vf(src, ref@mv) + L1 cost.
 // For 16-bit samples the variance at a full-pel MV is the sub-pel error routine at phase (0, 0)
@@ -506,7 +506,9 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
 template <typename T, int W>
 __device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
   if constexpr (sizeof(T) == 2 && VAR_VIA_SUBPEL_ROUTINE) {
-    return (int)bilinear_err<T, W>(S, r * 8, c * 8, 2) + sse_cost(S, r * 8, c * 8);
+    // vf(src, ref): the difference is src - ref, and the high-bitdepth rounding of the sum
+    // (ROUND_POWER_OF_TWO of a signed value) is not symmetric under negation -> mode 3
+    return (int)bilinear_err<T, W>(S, r * 8, c * 8, 3) + sse_cost(S, r * 8, c * 8);
   } else {
     unsigned sse;
     const int v = (int)variance<T, W>(S.src, S.stride, S.ref + r * S.stride + c, S.stride, S.hbd_shift, &sse);
@@ -860,15 +862,18 @@ __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2
   const int wr = iclamp(start.row, S.lim.row_min, S.lim.row_max);
   const int wc = iclamp(start.col, S.lim.col_min, S.lim.col_max);
   window_load<T, W>(S, winbuf, wr, wc);
+  // The window stays valid for the bilinear sub-pel search that follows (its candidates surround
+  // best_mv, normally inside the window); SUBPEL_TREE reuses the buffer as 8-tap scratch instead.
+  const bool keep = P.subpel_method != 0 && sizeof(T) == 2;
   if (P.use_skip) {
     if (!full_pixel_search_pass<T, W, true>(S, P, start, best_mv, winbuf)) {
-      S.win = nullptr;
+      if (!keep) S.win = nullptr;
       return;
     }
     if (S.wr != wr || S.wc != wc) window_load<T, W>(S, winbuf, wr, wc);
   }
   full_pixel_search_pass<T, W, false>(S, P, start, best_mv, winbuf);
-  S.win = nullptr;
+  if (!keep) S.win = nullptr;
 }
 
 // ---------------------------------------------------------------------------
@@ -876,8 +881,11 @@ __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2
 // ---------------------------------------------------------------------------
 // aom_sub_pixel_variance (aom_dsp/variance.c:91-139,150-163; hbd :478-560):
 // 2-tap bilinear over (W+1) x (W+1) samples then variance(filtered, src).
+// mode 1: sub-pel candidate (difference = filtered ref - src, as vf(pred, src) in mcomp.c:2385-2425);
+// mode 2: full-pel variance vf(ref, src); mode 3: full-pel variance vf(src, ref) (difference negated).
+// Modes 2 and 3 count as variance work in the instrumentation.
 template <typename T, int W>
-__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int ctr_idx) {
+__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int mode) {
   const Search<T> S = S_in;
   const int lane = lane_id();
   const int fr = r8 >> 3, fc = c8 >> 3;
@@ -934,8 +942,8 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
         acch = __dp2a_hi(md, pb, acch);                                // sum d * (d >> 8)
       }
     }
-    if (S.ctr && lane == 0) atomicAdd(&S.ctr[ctr_idx], (unsigned long long)(W * W));
-    int sum = (int)sumv - (int)sums;
+    if (S.ctr && lane == 0) atomicAdd(&S.ctr[mode == 1 ? 1 : 2], (unsigned long long)(W * W));
+    int sum = mode == 3 ? (int)sums - (int)sumv : (int)sumv - (int)sums;
     const unsigned long long sse64 = warp_sum_pair(sum, accl + (acch << 8));
     unsigned sse_out;
     return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
@@ -1140,9 +1148,14 @@ __device__ __noinline__ unsigned subpel_search(const Search<T> &S, const KParams
       hstep >>= 1;
     }
   } else {
-    unsigned sse;  // setup_center_error (mcomp.c:2718-2777): vf(ref, src)
-    sp.besterr = variance<T, W>(S.ref + start_full.row * S.stride + start_full.col, S.stride, S.src, S.stride,
-                                S.hbd_shift, &sse);
+    // setup_center_error (mcomp.c:2718-2777): vf(ref, src); the variance is symmetric in its arguments
+    if constexpr (sizeof(T) == 2 && VAR_VIA_SUBPEL_ROUTINE) {
+      sp.besterr = bilinear_err<T, W>(S, start.row, start.col, 2);
+    } else {
+      unsigned sse;
+      sp.besterr = variance<T, W>(S.ref + start_full.row * S.stride + start_full.col, S.stride, S.src, S.stride,
+                                  S.hbd_shift, &sse);
+    }
     const int rounds = P.allow_hp ? 3 : 2;
     for (int it = 0; it < rounds; it++) {
       const MV2 center = sp.best;

@@ -1,5 +1,7 @@
 """GPU: seeded random sweep of the parameter space (frame size, bit depth, chroma format, speed class,
 q, strength, window length / centre, motion, noise) -- CUDA path vs oracle, same bars as the fixed cases."""
+import os
+
 import numpy as np
 import pytest
 
@@ -35,7 +37,12 @@ def _case(seed):
     return W, H, N, bd, kw, clip, random_frames
 
 
-@pytest.mark.parametrize("seed", range(40))
+# TF_FUZZ_SEEDS=N widens the sweep for soak runs.  Seeds 115, 426 and 460 are the ones that exposed a
+# sign error in the high-bitdepth variance rounding (vf(src, ref) vs vf(ref, src)) during development.
+_SEEDS = sorted(set(range(int(os.environ.get("TF_FUZZ_SEEDS", "200")))) | {115, 426, 460})
+
+
+@pytest.mark.parametrize("seed", _SEEDS)
 def test_random_configuration(pkg, tfgpu, seed):
     W, H, N, bd, kw, clip, random_frames = _case(seed)
     fk = dict(ss_x=kw["ss_x"], ss_y=kw["ss_y"], monochrome=kw["monochrome"])
