@@ -1,4 +1,6 @@
 """CPU: the same seeded random sweep, oracle vs the compiled reference (skipped without oracle/_ref)."""
+import os
+
 import pytest
 
 import _clips
@@ -10,7 +12,8 @@ from test_gpu_fuzz import _case
 pytestmark = pytest.mark.skipif(not _ref.available(), reason="oracle/_ref/libtf_ref.so not built")
 
 
-@pytest.mark.parametrize("seed", range(40))
+# TF_FUZZ_SEEDS=N widens the sweep (soak runs); 115/426/460: see tests/test_gpu_fuzz.py
+@pytest.mark.parametrize("seed", sorted(set(range(int(os.environ.get("TF_FUZZ_SEEDS", "40")))) | {115, 426, 460}))
 def test_random_configuration_oracle_vs_reference(seed):
     W, H, N, bd, kw, clip, random_frames = _case(seed)
     fk = dict(ss_x=kw["ss_x"], ss_y=kw["ss_y"], monochrome=kw["monochrome"])
