@@ -62,8 +62,16 @@ struct tf_gpu_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // 16x16 searches overlap the 32x32 chain
   cudaStream_t copy_stream = nullptr;  // uploads overlap the search of earlier frames
-  cudaEvent_t done_ev = nullptr;       // end of the last submitted call (main stream)
-  bool done_valid = false;
+  cudaStream_t out_stream = nullptr;   // result read-back overlaps the search of the next window
+  cudaEvent_t ev_out_ready = nullptr;  // output complete on the device (main stream)
+  cudaEvent_t ev_out_done = nullptr;   // read-back of the device output finished (out stream)
+  bool out_done_valid = false;
+  // done_ev[e & 1] is recorded on the main stream at the end of call number e (every entry point that
+  // takes a new epoch), so it also covers every earlier call; uploads into a cache slot wait for the
+  // event that covers the call which used the slot last (see get_frame), not for the previous call,
+  // so the next window's uploads overlap the current window's kernels.
+  cudaEvent_t done_ev[2] = { nullptr, nullptr };
+  bool done_valid[2] = { false, false };
   cudaEvent_t ev_f32[TF_GPU_MAX_FRAMES] = {};
   cudaEvent_t ev_s16 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -112,6 +120,17 @@ int fail(tf_gpu_ctx *c, int code, const char *fmt, ...) {
   } while (0)
 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// Takes a new epoch for an entry point and records that epoch's completion event on the way out
+// (also on error paths, so done_ev[e & 1] never refers to a call older than e - 2).
+struct CallScope {
+  tf_gpu_ctx *ctx;
+  explicit CallScope(tf_gpu_ctx *c) : ctx(c) { ctx->epoch++; }
+  ~CallScope() {
+    const int i = (int)(ctx->epoch & 1);
+    if (ctx->done_ev[i] && cudaEventRecord(ctx->done_ev[i], ctx->stream) == cudaSuccess) ctx->done_valid[i] = true;
+  }
+};
 
 bool make_geometry(const tf_gpu_frame *f, int num_planes, Geometry *g, int luma_border = DEV_BORDER) {
   memset(g, 0, sizeof(*g));
@@ -164,9 +183,9 @@ int upload_frame(tf_gpu_ctx *ctx, DevFrame *d, const tf_gpu_frame *f) {
     CU(cudaMemcpy2DAsync(d->p00[p], (size_t)g.pitch[k] * es, f->plane[p], (size_t)f->stride[k] * es,
                          (size_t)g.crop_w[k] * es, g.crop_h[k], cudaMemcpyHostToDevice, ctx->copy_stream));
     const int ext_w = g.aligned_w[k] + g.bx[k], ext_h = g.aligned_h[k] + g.by[k];
-    const long long n = (long long)(g.bx[k] + ext_w) * (g.by[k] + ext_h);
+    const long long n = (long long)g.crop_h[k] * (g.bx[k] + ext_w - g.crop_w[k]) + (long long)(g.by[k] + ext_h - g.crop_h[k]) * (g.bx[k] + ext_w);
     const int threads = 256;
-    const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads);
+    const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads < 1 ? 1 : (n + threads - 1) / threads);
     if (g.is_hbd)
       extend_borders_kernel<uint16_t><<<blocks, threads, 0, ctx->copy_stream>>>((uint16_t *)d->p00[p], g.pitch[k],
                                                                           g.crop_w[k], g.crop_h[k], g.bx[k], g.by[k],
@@ -212,6 +231,7 @@ int get_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *f, int num_planes, DevFrame *
       else if (!s.valid) score = 2;
       else if (s.frame_id == 0) score = 3;
       else score = 4;
+      if (s.pinned_epoch + 1 == ctx->epoch) score += 10;  // read by the call that may still be running: last resort
       if (score < best_score || (score == best_score && victim && s.last_use < victim->last_use)) {
         best_score = score;
         victim = &s;
@@ -221,6 +241,13 @@ int get_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *f, int num_planes, DevFrame *
     int rc = alloc_dev_frame(ctx, victim, g);
     if (rc) return rc;
     victim->valid = false;
+    {
+      // kernels of the call that used this slot last (epoch pinned_epoch) must have finished:
+      // wait for the youngest recorded event that is not older than that call
+      const int idx = (victim->pinned_epoch + 1 >= ctx->epoch) ? (int)((ctx->epoch - 1) & 1) : (int)(ctx->epoch & 1);
+      if (victim->pinned_epoch > 0 && ctx->done_valid[idx])
+        CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev[idx], 0));
+    }
     rc = upload_frame(ctx, victim, f);
     if (rc) return rc;
     d = victim;
@@ -469,6 +496,8 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     }
     if (timed) cudaEventRecord(ctx->evk[1], ctx->stream);
   }
+  // the filter kernel overwrites the device output: the previous call's read-back must be over
+  if (ctx->out_done_valid) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out_done, 0));
   if (g.is_hbd) tf_filter_kernel<uint16_t><<<grid, FILT_THREADS, smem_filter, ctx->stream>>>(K);
   else tf_filter_kernel<uint8_t><<<grid, FILT_THREADS, smem_filter, ctx->stream>>>(K);
   nlaunch++;
@@ -493,7 +522,7 @@ int download_dump(tf_gpu_ctx *ctx, const tf_gpu_params *p, const Geometry &g, co
 }
 
 // Copy block rows [rb, re) of the device output into the caller's planes.
-int download_rows(tf_gpu_ctx *ctx, tf_gpu_frame *out, int rb, int re) {
+int download_rows(tf_gpu_ctx *ctx, tf_gpu_frame *out, int rb, int re, cudaStream_t os) {
   const Geometry &g = ctx->out.g;
   const size_t es = g.is_hbd ? 2 : 1;
   const int mb_cols = (g.crop_w[0] + 31) / 32;
@@ -513,35 +542,44 @@ int download_rows(tf_gpu_ctx *ctx, tf_gpu_frame *out, int rb, int re) {
     char *dst = (char *)out->plane[pl] + (size_t)y0 * out->stride[k] * es;
     const char *src = (const char *)ctx->out.p00[pl] + (size_t)y0 * g.pitch[k] * es;
     CU(cudaMemcpy2DAsync(dst, (size_t)out->stride[k] * es, src, (size_t)g.pitch[k] * es, (size_t)cols * es, y1 - y0,
-                         cudaMemcpyDeviceToHost, ctx->stream));
+                         cudaMemcpyDeviceToHost, os));
   }
   return TF_GPU_OK;
 }
 
 // aom_extend_frame_borders_c (aom_scale/generic/yv12extend.c:183-223) on the device output, then the
 // whole extended allocation (host border on every side) goes back in one 2-D copy per plane.
-int extend_and_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out) {
+int extend_and_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, cudaStream_t os) {
   const Geometry &g = ctx->out.g;
   const size_t es = g.is_hbd ? 2 : 1;
   for (int pl = 0; pl < g.num_planes; pl++) {
     const int k = pl > 0;
     const int hb_x = k ? out->border >> g.ss_x : out->border, hb_y = k ? out->border >> g.ss_y : out->border;
     const int ext_w = g.aligned_w[k] + hb_x, ext_h = g.aligned_h[k] + hb_y;  // right / bottom extents from pixel 0
-    const long long n = (long long)(hb_x + ext_w) * (hb_y + ext_h);
+    const long long n = (long long)g.crop_h[k] * (hb_x + ext_w - g.crop_w[k]) + (long long)(hb_y + ext_h - g.crop_h[k]) * (hb_x + ext_w);
     const int threads = 256;
-    const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads);
+    const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads < 1 ? 1 : (n + threads - 1) / threads);
+    if (!out->plane[pl]) return fail(ctx, TF_GPU_ERR_INVALID, "output plane %d is NULL", pl);
     if (g.is_hbd)
       extend_borders_kernel<uint16_t><<<blocks, threads, 0, ctx->stream>>>((uint16_t *)ctx->out.p00[pl], g.pitch[k], g.crop_w[k], g.crop_h[k], hb_x, hb_y, ext_w, ext_h);
     else
       extend_borders_kernel<uint8_t><<<blocks, threads, 0, ctx->stream>>>((uint8_t *)ctx->out.p00[pl], g.pitch[k], g.crop_w[k], g.crop_h[k], hb_x, hb_y, ext_w, ext_h);
     ctx->last_launches++;
-    if (!out->plane[pl]) return fail(ctx, TF_GPU_ERR_INVALID, "output plane %d is NULL", pl);
+  }
+  CU(cudaGetLastError());
+  if (os != ctx->stream) {
+    CU(cudaEventRecord(ctx->ev_out_ready, ctx->stream));
+    CU(cudaStreamWaitEvent(os, ctx->ev_out_ready, 0));
+  }
+  for (int pl = 0; pl < g.num_planes; pl++) {
+    const int k = pl > 0;
+    const int hb_x = k ? out->border >> g.ss_x : out->border, hb_y = k ? out->border >> g.ss_y : out->border;
+    const int ext_w = g.aligned_w[k] + hb_x, ext_h = g.aligned_h[k] + hb_y;
     char *dst = (char *)out->plane[pl] - ((size_t)hb_y * out->stride[k] + hb_x) * es;
     const char *src = (const char *)ctx->out.p00[pl] - ((size_t)hb_y * g.pitch[k] + hb_x) * es;
     CU(cudaMemcpy2DAsync(dst, (size_t)out->stride[k] * es, src, (size_t)g.pitch[k] * es, (size_t)(hb_x + ext_w) * es,
-                         hb_y + ext_h, cudaMemcpyDeviceToHost, ctx->stream));
+                         hb_y + ext_h, cudaMemcpyDeviceToHost, os));
   }
-  CU(cudaGetLastError());
   return TF_GPU_OK;
 }
 
@@ -553,10 +591,8 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
   if (!frames || !out) return fail(ctx, TF_GPU_ERR_INVALID, "frames/out is NULL");
   CU(cudaSetDevice(ctx->device));
   if ((int)ctx->cache.size() < params->num_frames) return fail(ctx, TF_GPU_ERR_MEM, "frame cache smaller than the window");
-  ctx->epoch++;
+  CallScope scope(ctx);
   ctx->last_launches = 0;
-  // cache slots may still be read by the kernels of the previous (asynchronous) call
-  if (ctx->done_valid) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev, 0));
   DevFrame *devf[TF_GPU_MAX_FRAMES];
   // upload order = consumption order: the frame to filter first, then the chain order
   for (int k = 0; k < params->num_frames; k++) {
@@ -596,21 +632,30 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
     rb = params->out_row_begin < 0 ? 0 : params->out_row_begin;
     re = params->out_row_end > mb_rows ? mb_rows : params->out_row_end;
   }
+  // the result goes back on its own stream so that the next window's search is not held up by
+  // the copy (debug dumps keep everything on the main stream)
+  cudaStream_t os = dump ? ctx->stream : ctx->out_stream;
   if (extend_out) {
-    rc = extend_and_download_output(ctx, out);
+    rc = extend_and_download_output(ctx, out, os);
     if (rc) return rc;
   } else {
-    rc = download_rows(ctx, out, rb, re);
+    if (os != ctx->stream) {
+      CU(cudaEventRecord(ctx->ev_out_ready, ctx->stream));
+      CU(cudaStreamWaitEvent(os, ctx->ev_out_ready, 0));
+    }
+    rc = download_rows(ctx, out, rb, re, os);
     if (rc) return rc;
   }
   if (dump) {
     rc = download_dump(ctx, params, g, dump);
     if (rc) return rc;
   }
-  CU(cudaMemcpyAsync(ctx->h_diff + 2 * slot, d_diff, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaEventRecord(t.ev, ctx->stream));
-  CU(cudaEventRecord(ctx->done_ev, ctx->stream));
-  ctx->done_valid = true;
+  CU(cudaMemcpyAsync(ctx->h_diff + 2 * slot, d_diff, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, os));
+  CU(cudaEventRecord(t.ev, os));
+  if (os != ctx->stream) {
+    CU(cudaEventRecord(ctx->ev_out_done, os));
+    ctx->out_done_valid = true;
+  }
   t.id = ctx->next_ticket++;
   t.diff_dst = diff_sum_sse;
   t.want_diff = diff_sum_sse != nullptr;
@@ -656,7 +701,11 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out_ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out_done, cudaEventDisableTiming);
+  for (int i = 0; i < 2; i++)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->done_ev[i], cudaEventDisableTiming);
   for (auto &d : ctx->cache)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ready, cudaEventDisableTiming);
   for (int i = 0; i < TF_GPU_MAX_FRAMES && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->ev_f32[i], cudaEventDisableTiming);
@@ -694,13 +743,18 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->out_stream) cudaStreamSynchronize(ctx->out_stream);
   for (auto &d : ctx->cache) {
     for (int p = 0; p < 3; p++)
       if (d.base[p]) cudaFree(d.base[p]);
     if (d.ready) cudaEventDestroy(d.ready);
   }
-  if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
+  for (int i = 0; i < 2; i++)
+    if (ctx->done_ev[i]) cudaEventDestroy(ctx->done_ev[i]);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
+  if (ctx->ev_out_ready) cudaEventDestroy(ctx->ev_out_ready);
+  if (ctx->ev_out_done) cudaEventDestroy(ctx->ev_out_done);
   for (int p = 0; p < 3; p++)
     if (ctx->out.base[p]) cudaFree(ctx->out.base[p]);
   for (int i = 0; i < 10; i++)
@@ -735,10 +789,9 @@ int tf_gpu_cache_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *frame) {
   if (!ctx || !frame) return TF_GPU_ERR_INVALID;
   if (!frame->frame_id) return fail(ctx, TF_GPU_ERR_INVALID, "frame_id 0 cannot be cached");
   CU(cudaSetDevice(ctx->device));
-  ctx->epoch++;
+  CallScope scope(ctx);
   DevFrame *d;
   const int num_planes = frame->plane[1] ? 3 : 1;
-  if (ctx->done_valid) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev, 0));
   int rc = get_frame(ctx, frame, num_planes, &d);
   if (rc) return rc;
   CU(cudaStreamSynchronize(ctx->copy_stream));
@@ -757,12 +810,11 @@ int tf_gpu_estimate_noise(tf_gpu_ctx *ctx, const tf_gpu_frame *frame, int plane,
   if (!ctx || !frame || !noise_level) return TF_GPU_ERR_INVALID;
   if (plane < 0 || plane > 2) return fail(ctx, TF_GPU_ERR_INVALID, "plane out of range");
   CU(cudaSetDevice(ctx->device));
-  ctx->epoch++;
+  CallScope scope(ctx);
   ctx->last_launches = 0;
   DevFrame *d;
   const int num_planes = frame->plane[1] ? 3 : 1;
   if (plane >= num_planes) return fail(ctx, TF_GPU_ERR_INVALID, "plane not present");
-  if (ctx->done_valid) CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->done_ev, 0));
   int rc = get_frame(ctx, frame, num_planes, &d);
   if (rc) return rc;
   CU(cudaStreamWaitEvent(ctx->stream, d->ready, 0));
@@ -831,7 +883,7 @@ int tf_gpu_filter_resident_async(tf_gpu_ctx *ctx, const tf_gpu_params *params, c
   int rc = validate_params(ctx, params);
   if (rc) return rc;
   CU(cudaSetDevice(ctx->device));
-  ctx->epoch++;
+  CallScope scope(ctx);
   ctx->last_launches = 0;
   DevFrame *devf[TF_GPU_MAX_FRAMES];
   for (int i = 0; i < params->num_frames; i++) {
@@ -885,7 +937,7 @@ int tf_gpu_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, int row_begin, in
   }
   if (row_begin < 0) row_begin = 0;
   if (row_end > mb_rows) row_end = mb_rows;
-  int rc = download_rows(ctx, out, row_begin, row_end);
+  int rc = download_rows(ctx, out, row_begin, row_end, ctx->stream);
   if (rc) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   return TF_GPU_OK;
@@ -971,6 +1023,8 @@ int tf_gpu_synchronize(tf_gpu_ctx *ctx) {
   if (!ctx) return TF_GPU_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->out_stream));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
   return TF_GPU_OK;
 }
 

@@ -1675,12 +1675,23 @@ __global__ void __launch_bounds__(FILT_THREADS, 6) tf_filter_kernel(const __grid
 template <typename T>
 __global__ void extend_borders_kernel(T *plane /* pixel (0,0) */, int pitch, int crop_w, int crop_h, int bx, int by,
                                       int ext_w /* samples right of x=0 incl. crop */, int ext_h) {
-  const int tw = bx + ext_w;  // total columns covered
-  const int th = by + ext_h;
-  const long long n = (long long)tw * th;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int y = (int)(i / tw) - by, x = (int)(i % tw) - bx;
-    if (x >= 0 && x < crop_w && y >= 0 && y < crop_h) continue;
+  // Only the samples outside the crop rectangle are visited: the side strips of the crop rows
+  // first, then the full-width rows above and below.
+  const int tw = bx + ext_w;                // total columns covered
+  const int sw = bx + (ext_w - crop_w);     // strip samples per crop row (left + right)
+  const int n_side = crop_h * sw;
+  const int n = n_side + (by + ext_h - crop_h) * tw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int x, y;
+    if (i < n_side) {
+      y = i / sw;
+      const int xx = i - y * sw;
+      x = xx < bx ? xx - bx : crop_w + (xx - bx);
+    } else {
+      const int j = i - n_side, ry = j / tw;
+      x = j - ry * tw - bx;
+      y = ry < by ? ry - by : crop_h + (ry - by);
+    }
     const int sx = iclamp(x, 0, crop_w - 1), sy = iclamp(y, 0, crop_h - 1);
     plane[(long long)y * pitch + x] = plane[(long long)sy * pitch + sx];
   }

@@ -111,6 +111,31 @@ def test_async_submit_wait(pkg, tfgpu):
         assert (o.full_blocks(0) == full["out"][0]).all()
 
 
+@pytest.mark.parametrize("slots", [0, 24], ids=["default-cache", "smallest-cache"])
+def test_pipelined_submits_of_different_windows(pkg, slots):
+    """Several different windows submitted back to back on one context (uploads of window k+1
+    overlap the kernels of window k; uncached frames, id 0).  With the smallest cache (24 slots,
+    15-frame windows) the second window has to reuse slots of the window still in flight, which
+    must wait for it."""
+    W, H, N = 320, 192, 15
+    ctx = pkg.TemporalFilterGpu(max_cached_frames=slots)
+    try:
+        p = _params.tf_params(W, H, N, bit_depth=10)
+        wins = [_clips.moving_texture(W, H, N, 10, seed=900 + k, motion=(k % 3, 1 + k % 4)) for k in range(5)]
+        want = [_gpu.run_gpu(pkg, ctx, p, fr, dump=False) for fr in wins]
+        bufs = [_bufs(pkg, p, fr, 0) for fr in wins]
+        for rep in range(2):
+            outs = [pkg.Yv12Buffer(W, H, 1, 1, True, p["border"]) for _ in wins]
+            tickets = [ctx.submit(p, b, o) for b, o in zip(bufs, outs)]
+            for (t, diff, _keep), o, w in zip(tickets, outs, want):
+                ctx.wait(t)
+                assert [diff[0], diff[1]] == list(w["diff"])
+                for pl in range(3):
+                    assert (o.full_blocks(pl) == w["out"][pl]).all()
+    finally:
+        ctx.close()
+
+
 def test_invalid_arguments_return_errors(pkg, tfgpu):
     W, H, N = 64, 64, 3
     frames = _clips.moving_texture(W, H, N, 8)
