@@ -505,7 +505,7 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
 // shared-memory window whenever the MV lies inside it instead of from global memory.
 template <typename T, int W>
 __device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
-  if constexpr (sizeof(T) == 2 && VAR_VIA_SUBPEL_ROUTINE) {
+  if constexpr (VAR_VIA_SUBPEL_ROUTINE) {
     // vf(src, ref): the difference is src - ref, and the high-bitdepth rounding of the sum
     // (ROUND_POWER_OF_TWO of a signed value) is not symmetric under negation -> mode 3
     return (int)bilinear_err<T, W>(S, r * 8, c * 8, 3) + sse_cost(S, r * 8, c * 8);
@@ -864,7 +864,7 @@ __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2
   window_load<T, W>(S, winbuf, wr, wc);
   // The window stays valid for the bilinear sub-pel search that follows (its candidates surround
   // best_mv, normally inside the window); SUBPEL_TREE reuses the buffer as 8-tap scratch instead.
-  const bool keep = P.subpel_method != 0 && sizeof(T) == 2;
+  const bool keep = P.subpel_method != 0;
   if (P.use_skip) {
     if (!full_pixel_search_pass<T, W, true>(S, P, start, best_mv, winbuf)) {
       if (!keep) S.win = nullptr;
@@ -981,7 +981,8 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
       sse += (unsigned)(d * d);
     }
   }
-  if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(W * W));
+  if (S.ctr && lane == 0) atomicAdd(&S.ctr[mode == 1 ? 1 : 2], (unsigned long long)(W * W));
+  if (mode == 3) sum = -sum;
   const unsigned long long sse64 = warp_sum_pair(sum, sse);
   unsigned sse_out;
   return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
@@ -1149,7 +1150,7 @@ __device__ __noinline__ unsigned subpel_search(const Search<T> &S, const KParams
     }
   } else {
     // setup_center_error (mcomp.c:2718-2777): vf(ref, src); the variance is symmetric in its arguments
-    if constexpr (sizeof(T) == 2 && VAR_VIA_SUBPEL_ROUTINE) {
+    if constexpr (VAR_VIA_SUBPEL_ROUTINE) {
       sp.besterr = bilinear_err<T, W>(S, start.row, start.col, 2);
     } else {
       unsigned sse;
