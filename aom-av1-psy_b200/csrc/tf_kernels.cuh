@@ -890,103 +890,77 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
   const int lane = lane_id();
   const int fr = r8 >> 3, fc = c8 >> 3;
   const int xo = c8 & 7, yo = r8 & 7;
-  if constexpr (sizeof(T) == 2) {
-    // 16-bit samples, two per 32-bit register.  The taps {128 - 16k, 16k} share the factor 16, so
-    // ROUND_POWER_OF_TWO(a0 * (128 - 16k) + a1 * 16k, 7) == (a0 * (8 - k) + a1 * k + 4) >> 3 exactly,
-    // and with samples <= 4095 every term stays below 2^16: both halves of a register go through one
-    // IMAD without carrying into each other.  Lane = (row band, column pair).
-    constexpr int PAIRS = W / 2;          // lanes per block row
-    constexpr int BANDS = 32 / PAIRS;     // 2 (W = 32) or 4 (W = 16)
-    constexpr int BROWS = W / BANDS;      // 16 or 4 rows per band
-    constexpr int CH = BROWS < 8 ? BROWS : 8;
-    const int j = lane % PAIRS, rbeg = (lane / PAIRS) * BROWS;
-    const SadSrc Q = sad_src(S, window_covers(S, fr, fc, 1) && S.wr - fr < S.wR && S.wc - fc < S.wR);
-    const uintptr_t a = reinterpret_cast<uintptr_t>(Q.base + (fr + rbeg) * Q.pitchB + (fc + 2 * j) * 2);
-    const unsigned char *wb = reinterpret_cast<const unsigned char *>(a & ~(uintptr_t)3);
-    const unsigned sh = (unsigned)(a & 2) * 8;  // row pitches are multiples of 4 bytes: same for every row
-    const uint32_t *sp = reinterpret_cast<const uint32_t *>(S.src + rbeg * S.stride + 2 * j);
-    const int sstep = S.stride / 2;
-    const unsigned m0 = 8 - xo, m1 = xo, n0 = 8 - yo, n1 = yo;
-    constexpr unsigned RND = 0x00040004u, MSK = 0x1fff1fffu;
-    auto hrow = [&](uint32_t w0, uint32_t w1) -> unsigned {
-      const unsigned A = __funnelshift_rc(w0, w1, sh), B = __funnelshift_rc(w0, w1, sh + 16);
-      return ((A * m0 + (B * m1 + RND)) >> 3) & MSK;
-    };
-    unsigned hprev;
-    {
-      const uint32_t *wp = reinterpret_cast<const uint32_t *>(wb);
-      hprev = hrow(wp[0], wp[1]);
-    }
-    unsigned sumv = 0, sums = 0, accl = 0, acch = 0;
-#pragma unroll 1
-    for (int t0 = 0; t0 < BROWS; t0 += CH) {
-      uint32_t w0[CH], w1[CH], sv[CH];
-#pragma unroll
-      for (int k = 0; k < CH; k++) {  // all loads of a chunk are issued before use
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(wb + (t0 + k + 1) * Q.pitchB);
-        w0[k] = wp[0];
-        w1[k] = wp[1];
-      }
-#pragma unroll
-      for (int k = 0; k < CH; k++) sv[k] = __ldg(sp + (t0 + k) * sstep);
-#pragma unroll
-      for (int k = 0; k < CH; k++) {
-        const unsigned hn = hrow(w0[k], w1[k]);
-        const unsigned v = ((hprev * n0 + (hn * n1 + RND)) >> 3) & MSK;
-        hprev = hn;
-        sumv = __dp2a_lo(v, 0x0101u, sumv);
-        sums = __dp2a_lo(sv[k], 0x0101u, sums);
-        const unsigned md = __vmaxu2(v, sv[k]) - __vminu2(v, sv[k]);  // |v - s| per half
-        const unsigned pb = __byte_perm(md, 0, 0x3120);                // (d0.lo, d1.lo, d0.hi, d1.hi)
-        accl = __dp2a_lo(md, pb, accl);                                // sum d * (d & 255)
-        acch = __dp2a_hi(md, pb, acch);                                // sum d * (d >> 8)
-      }
-    }
-    if (S.ctr && lane == 0) atomicAdd(&S.ctr[mode == 1 ? 1 : 2], (unsigned long long)(W * W));
-    int sum = mode == 3 ? (int)sums - (int)sumv : (int)sumv - (int)sums;
-    const unsigned long long sse64 = warp_sum_pair(sum, accl + (acch << 8));
-    unsigned sse_out;
-    return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
-  } else {
-  const int f0 = 128 - 16 * xo, f1 = 16 * xo, g0 = 128 - 16 * yo, g1 = 16 * yo;
-  constexpr int BANDS = 32 / W;      // 1 (W=32) or 2 (W=16)
-  constexpr int BROWS = W / BANDS;   // rows per band
-  constexpr int CH = 8;              // rows per chunk: all loads of a chunk are issued before use
-  const int col = lane % W, band = lane / W;
-  const int rbeg = band * BROWS;
+  // Two samples per 32-bit register (16-bit halves; 8-bit samples are widened on load).  The taps
+  // {128 - 16k, 16k} share the factor 16, so
+  // ROUND_POWER_OF_TWO(a0 * (128 - 16k) + a1 * 16k, 7) == (a0 * (8 - k) + a1 * k + 4) >> 3 exactly,
+  // and with samples <= 4095 every term stays below 2^16: both halves of a register go through one
+  // IMAD without carrying into each other.  Lane = (row band, column pair).
+  constexpr int ES = (int)sizeof(T);
+  constexpr int PAIRS = W / 2;          // lanes per block row
+  constexpr int BANDS = 32 / PAIRS;     // 2 (W = 32) or 4 (W = 16)
+  constexpr int BROWS = W / BANDS;      // 16 or 4 rows per band
+  constexpr int CH = BROWS < 8 ? BROWS : 8;
+  const int j = lane % PAIRS, rbeg = (lane / PAIRS) * BROWS;
   // (fr, fc) and (fr + 1, fc + 1) inside the search window -> read it from shared memory
   const SadSrc Q = sad_src(S, window_covers(S, fr, fc, 1) && S.wr - fr < S.wR && S.wc - fc < S.wR);
-  const unsigned char *rb = Q.base + (fr + rbeg) * Q.pitchB + (fc + col) * (int)sizeof(T);
-  const T *sp = S.src + rbeg * S.stride + col;
-  int sum = 0;
-  unsigned sse = 0;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(Q.base + (fr + rbeg) * Q.pitchB + (fc + 2 * j) * ES);
+  const unsigned char *wb = reinterpret_cast<const unsigned char *>(a & ~(uintptr_t)3);
+  const unsigned sh = (unsigned)(a & 3) * 8;  // row pitches are multiples of 4 bytes: same for every row
+  const int sstep = S.stride / 2;             // source row step in pairs
+  const unsigned m0 = 8 - xo, m1 = xo, n0 = 8 - yo, n1 = yo;
+  constexpr unsigned RND = 0x00040004u, MSK = 0x1fff1fffu;
+  auto hrow = [&](uint32_t w0, uint32_t w1) -> unsigned {
+    unsigned A, B;  // samples (x, x + 1) and (x + 1, x + 2)
+    if (ES == 2) {
+      A = __funnelshift_rc(w0, w1, sh);
+      B = __funnelshift_rc(w0, w1, sh + 16);
+    } else {
+      const unsigned x = __funnelshift_r(w0, w1, sh);  // bytes x .. x + 3
+      A = __byte_perm(x, 0, 0x4140);
+      B = __byte_perm(x, 0, 0x4241);
+    }
+    return ((A * m0 + (B * m1 + RND)) >> 3) & MSK;
+  };
+  auto src_pair = [&](int r) -> unsigned {
+    if (ES == 2) return __ldg(reinterpret_cast<const uint32_t *>(S.src + rbeg * S.stride + 2 * j) + r * sstep);
+    const unsigned s = __ldg(reinterpret_cast<const uint16_t *>(S.src + rbeg * S.stride + 2 * j) + r * sstep);
+    return __byte_perm(s, 0, 0x4140);
+  };
+  unsigned hprev;
+  {
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(wb);
+    hprev = hrow(wp[0], wp[1]);
+  }
+  unsigned sumv = 0, sums = 0, accl = 0, acch = 0;
 #pragma unroll 1
   for (int t0 = 0; t0 < BROWS; t0 += CH) {
-    int h[CH + 1], sv[CH];
+    uint32_t w0[CH], w1[CH], sv[CH];
 #pragma unroll
-    for (int k = 0; k <= CH; k++) {
-      const T *rp = reinterpret_cast<const T *>(rb + (t0 + k) * Q.pitchB);
-      const int a0 = (k < CH || yo) ? (int)rp[0] : 0;
-      const int a1 = (xo && (k < CH || yo)) ? (int)rp[1] : 0;
-      h[k] = xo ? rpot(a0 * f0 + a1 * f1, 7) : a0;
+    for (int k = 0; k < CH; k++) {  // all loads of a chunk are issued before use
+      const uint32_t *wp = reinterpret_cast<const uint32_t *>(wb + (t0 + k + 1) * Q.pitchB);
+      w0[k] = wp[0];
+      w1[k] = wp[1];
     }
 #pragma unroll
-    for (int k = 0; k < CH; k++) sv[k] = (int)__ldg(sp + (t0 + k) * S.stride);
+    for (int k = 0; k < CH; k++) sv[k] = src_pair(t0 + k);
 #pragma unroll
     for (int k = 0; k < CH; k++) {
-      int v = yo ? rpot(h[k] * g0 + h[k + 1] * g1, 7) : h[k];
-      if (sizeof(T) == 1) v &= 0xff;
-      const int d = v - sv[k];
-      sum += d;
-      sse += (unsigned)(d * d);
+      const unsigned hn = hrow(w0[k], w1[k]);
+      const unsigned v = ((hprev * n0 + (hn * n1 + RND)) >> 3) & MSK;
+      hprev = hn;
+      sumv = __dp2a_lo(v, 0x0101u, sumv);
+      sums = __dp2a_lo(sv[k], 0x0101u, sums);
+      const unsigned md = __vmaxu2(v, sv[k]) - __vminu2(v, sv[k]);  // |v - s| per half
+      const unsigned pb = __byte_perm(md, 0, 0x3120);                // (d0.lo, d1.lo, d0.hi, d1.hi)
+      accl = __dp2a_lo(md, pb, accl);                                // sum d * (d & 255)
+      if (ES == 2) acch = __dp2a_hi(md, pb, acch);                   // sum d * (d >> 8)
     }
   }
   if (S.ctr && lane == 0) atomicAdd(&S.ctr[mode == 1 ? 1 : 2], (unsigned long long)(W * W));
-  if (mode == 3) sum = -sum;
-  const unsigned long long sse64 = warp_sum_pair(sum, sse);
+  int sum = mode == 3 ? (int)sums - (int)sumv : (int)sumv - (int)sums;
+  const unsigned long long sse64 = warp_sum_pair(sum, accl + (acch << 8));
   unsigned sse_out;
   return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
-  }
 }
 
 __device__ __forceinline__ int clip_px(int v, int bd) {
