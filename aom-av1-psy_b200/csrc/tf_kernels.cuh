@@ -10,16 +10,16 @@
 //                       (frame, block, sub-block) task -- 56x more parallelism
 //                       than blocks for a 15-frame window;
 //   tf_filter_kernel    partition decision, 12-tap predictor, weights,
-//                       accumulate/count, normalise, FRAME_DIFF: pred / accum /
-//                       count never leave shared memory.
+//                       accumulate/count, normalise, FRAME_DIFF: four warps per
+//                       block; pred / accum / count never leave shared memory.
 // Every data-dependent decision of the reference's search is replayed
 // warp-uniformly (all lanes take the same branch after a shuffle reduction), so
 // motion vectors are bit-exact by construction.
 //
 // Integer work is byte/halfword SIMD-in-word: VABSDIFF4.U8.ACC (__vsadu4) for
-// 8-bit SAD, VIMNMX.U16x2 (max-min) for high-bitdepth SAD, IDP.4A for
-// sum/sum-of-squares.  No tensor cores: nothing on this path is a dense
-// contraction.
+// 8-bit SAD, VIMNMX.U16x2 (max-min) for high-bitdepth SAD, one IMAD per two
+// samples for the bilinear taps, IDP.2A for sums / sums of squares.  No tensor
+// cores: nothing on this path is a dense contraction.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -100,11 +100,6 @@ template <int N>
 __device__ __forceinline__ unsigned seg_reduce_u32(unsigned v) {
 #pragma unroll
   for (int o = N / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-  return v;
-}
-__device__ __forceinline__ int warp_sum_i32(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
@@ -403,35 +398,7 @@ __device__ __forceinline__ void far_load_src(const T *src, int stride, int lane,
     sf[it] = __ldg(reinterpret_cast<const uint32_t *>(src + (it * F::RPI + rr) * F::RSTEP * stride) + j);
 }
 
-// Partial (per-lane) SAD of the candidate at (r, c) read from global memory.
-template <typename T, int W, bool SKIP>
-__device__ __forceinline__ unsigned far_partial(const T *ref, int stride, int r, int c, int lane,
-                                                const uint32_t (&sf)[FarL<T, W, SKIP>::IT]) {
-  using F = FarL<T, W, SKIP>;
-  const int j = lane % F::NW, rr = lane / F::NW;
-  const T *p = ref + (r + rr * F::RSTEP) * stride + c;
-  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3) + j;
-  const unsigned sh = (unsigned)(a & 3) * 8;
-  const int step_words = F::RPI * F::RSTEP * stride * (int)sizeof(T) / 4;
-  uint32_t w0[F::IT], w1[F::IT];
-#pragma unroll
-  for (int it = 0; it < F::IT; it++) {
-    w0[it] = __ldg(wp + it * step_words);
-    w1[it] = __ldg(wp + it * step_words + 1);
-  }
-  unsigned s = 0;
-#pragma unroll
-  for (int it = 0; it < F::IT; it++) {
-    const unsigned x = __funnelshift_r(w0[it], w1[it], sh);
-    if (sizeof(T) == 1) s = __vsadu4(x, sf[it]) + s;
-    else s += __vmaxu2(x, sf[it]) - __vminu2(x, sf[it]);  // packed u16 lanes: IT <= 16 terms of <= 4095, no carry
-  }
-  if (sizeof(T) != 1) s = (s & 0xffffu) + (s >> 16);
-  return s;
-}
-
-// Same, with the candidate given as a byte offset from a per-lane base pointer
+// Partial (per-lane) SAD of a far candidate, given as a byte offset from a per-lane base pointer
 // (base = ref + this lane's row offset + word column), so the per-candidate address
 // arithmetic is one 64-bit add.
 template <typename T, int W, bool SKIP>
