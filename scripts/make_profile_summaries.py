@@ -1,6 +1,9 @@
 """Turns gpurun_out/{launches_R.csv, prof_R_<kernel>.ncu-rep} into the tracked summaries under profiles/."""
 import collections, csv, json, os, subprocess, sys
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
+# optional second argument: "1080p8" for the captures of scripts/gpu_prof_1080p8.sh
+TAG = sys.argv[2] if len(sys.argv) > 2 else ""
+WL, WLNAME, WLDESC = (("1080p8", "1080p8_n7", "1080p 8-bit 4:2:0, N=7") if TAG == "1080p8" else ("4k10", "4k10_n15", "4K 10-bit 4:2:0, N=15"))
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out = os.path.join(root, "profiles")
 os.makedirs(out, exist_ok=True)
@@ -32,15 +35,15 @@ keys = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__throughput.avg.pct_of_peak_sustained_elapsed']
 traffic = {}
 for kname in ("tf_search32", "tf_search16", "tf_filter"):
-    rep = os.path.join(root, "gpurun_out", f"prof_{R}_{kname}.ncu-rep")
+    rep = os.path.join(root, "gpurun_out", f"prof_{R}_{TAG + '_' if TAG else ''}{kname}.ncu-rep")
     if not os.path.exists(rep):
         continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
-    with open(os.path.join(out, f"ncu_{R}_{kname}_4k10.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kname}  (4K 10-bit 4:2:0, N=15, one launch)\n")
+    with open(os.path.join(out, f"ncu_{R}_{kname}_{WL}.txt"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kname}  ({WLDESC}, one launch)\n")
         for k in keys:
             if k in d:
                 f.write(f"{k} = {d[k][0]} {d[k][1]}\n")
@@ -70,7 +73,7 @@ for kname in ("tf_search32", "tf_search16", "tf_filter"):
 if traffic:
     p = os.path.join(out, "traffic_r01.json")
     cur = json.load(open(p)) if os.path.exists(p) else {}
-    cur.setdefault("4k10_n15", {}).update(traffic)
+    cur.setdefault(WLNAME, {}).update(traffic)
     cur["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full (per-frame launches for the search kernels)"
     json.dump(cur, open(p, "w"), indent=1)
 print(open(os.path.join(out, f"launches_{R}_summary.txt")).read() if os.path.exists(os.path.join(out, f"launches_{R}_summary.txt")) else "")
