@@ -930,6 +930,109 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
   return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
 }
 
+// The four first-level candidates of a sub-pel round (left, right, up, down of (tr, tc) at distance
+// hstep; first_level_check, mcomp.c:2503-2541) evaluated in one pass: their errors do not depend on the
+// incumbent, so the reference's sequential comparisons can be replayed on the four results afterwards.
+// Lane group g = lane / 8 evaluates candidate g; a lane owns one (W = 16) or two (W = 32) column pairs
+// over all rows, so there is no band overhead and one reduction / variance epilogue serves all four.
+// Candidates whose bit in validmask is clear are not read (their group re-reads the centre) and
+// return INT_MAX.  Same packed arithmetic as bilinear_err.
+template <typename T, int W>
+__device__ __noinline__ uint4 bilinear_err4(const Search<T> &S_in, int tr, int tc, int hstep, unsigned validmask) {
+  const Search<T> S = S_in;
+  constexpr int ES = (int)sizeof(T);
+  constexpr int NP = W / 16;            // column pairs per lane
+  constexpr int CH = NP == 1 ? 8 : 4;   // rows per chunk: all loads of a chunk are issued before use
+  const int lane = lane_id(), g = lane >> 3, u = lane & 7;
+  const bool valid = (validmask >> g) & 1u;
+  int r8 = tr, c8 = tc;
+  if (valid) {
+    if (g == 0) c8 -= hstep;
+    else if (g == 1) c8 += hstep;
+    else if (g == 2) r8 -= hstep;
+    else r8 += hstep;
+  }
+  const int fr = r8 >> 3, fc = c8 >> 3;
+  const unsigned xo = c8 & 7, yo = r8 & 7;
+  // all four candidates and their +1 row / column lie within one full-pel step of the centre
+  const SadSrc Q = sad_src(S, window_covers(S, tr >> 3, tc >> 3, 2));
+  const uintptr_t a = reinterpret_cast<uintptr_t>(Q.base + fr * Q.pitchB + (fc + 2 * u) * ES);
+  const unsigned char *wb = reinterpret_cast<const unsigned char *>(a & ~(uintptr_t)3);
+  const unsigned sh = (unsigned)(a & 3) * 8;  // 16 pairs further on is a multiple of 4 bytes: same shift
+  const int sstep = S.stride / 2;
+  const unsigned m0 = 8 - xo, m1 = xo, n0 = 8 - yo, n1 = yo;
+  constexpr unsigned RND = 0x00040004u, MSK = 0x1fff1fffu;
+  auto hrow = [&](uint32_t w0, uint32_t w1) -> unsigned {
+    unsigned A, B;
+    if (ES == 2) {
+      A = __funnelshift_rc(w0, w1, sh);
+      B = __funnelshift_rc(w0, w1, sh + 16);
+    } else {
+      const unsigned x = __funnelshift_r(w0, w1, sh);
+      A = __byte_perm(x, 0, 0x4140);
+      B = __byte_perm(x, 0, 0x4241);
+    }
+    return ((A * m0 + (B * m1 + RND)) >> 3) & MSK;
+  };
+  auto src_pair = [&](int r, int p) -> unsigned {
+    if (ES == 2) return __ldg(reinterpret_cast<const uint32_t *>(S.src + 2 * (u + 8 * p)) + r * sstep);
+    const unsigned s = __ldg(reinterpret_cast<const uint16_t *>(S.src + 2 * (u + 8 * p)) + r * sstep);
+    return __byte_perm(s, 0, 0x4140);
+  };
+  unsigned hprev[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(wb + p * 16 * ES);
+    hprev[p] = hrow(wp[0], wp[1]);
+  }
+  unsigned sumv = 0, sums = 0, accl = 0, acch = 0;
+#pragma unroll 1
+  for (int t0 = 0; t0 < W; t0 += CH) {
+    uint32_t w0[CH][NP], w1[CH][NP], sv[CH][NP];
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(wb + (t0 + k + 1) * Q.pitchB + p * 16 * ES);
+        w0[k][p] = wp[0];
+        w1[k][p] = wp[1];
+      }
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+#pragma unroll
+      for (int p = 0; p < NP; p++) sv[k][p] = src_pair(t0 + k, p);
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        const unsigned hn = hrow(w0[k][p], w1[k][p]);
+        const unsigned v = ((hprev[p] * n0 + (hn * n1 + RND)) >> 3) & MSK;
+        hprev[p] = hn;
+        sumv = __dp2a_lo(v, 0x0101u, sumv);
+        sums = __dp2a_lo(sv[k][p], 0x0101u, sums);
+        const unsigned md = __vmaxu2(v, sv[k][p]) - __vminu2(v, sv[k][p]);
+        const unsigned pb = __byte_perm(md, 0, 0x3120);
+        accl = __dp2a_lo(md, pb, accl);
+        if (ES == 2) acch = __dp2a_hi(md, pb, acch);
+      }
+  }
+  if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(__popc(validmask & 15u) * W * W));
+  // (sum, sse) of a candidate = totals over its 8 lanes: |sum| < 2^19 per lane, so sum + 2^19 is
+  // non-negative and 8 of them stay below 2^24; sse totals < 2^35
+  unsigned long long pk = ((unsigned long long)(accl + (acch << 8)) << 24) | (unsigned)((int)sumv - (int)sums + (1 << 19));
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) pk += __shfl_xor_sync(FULL, pk, o);
+  const int sum = (int)(pk & 0xffffffu) - (1 << 22);
+  unsigned sse_out;
+  const unsigned mine = valid ? var_finish(sum, pk >> 24, W, S.hbd_shift, &sse_out) : (unsigned)INT_MAX_;
+  uint4 out;
+  out.x = __shfl_sync(FULL, mine, 0);
+  out.y = __shfl_sync(FULL, mine, 8);
+  out.z = __shfl_sync(FULL, mine, 16);
+  out.w = __shfl_sync(FULL, mine, 24);
+  return out;
+}
+
 __device__ __forceinline__ int clip_px(int v, int bd) {
   const int m = (1 << bd) - 1;
   return v < 0 ? 0 : (v > m ? m : v);
@@ -1019,10 +1122,30 @@ __device__ __forceinline__ unsigned check_better(Subpel<T, W> &sp, int r8, int c
 // first_level_check(_fast) (mcomp.c:2503-2541, 2626-2660)
 template <typename T, int W>
 __device__ MV2 first_level(Subpel<T, W> &sp, MV2 t, int hstep, bool accurate) {
-  const unsigned left = check_better(sp, t.row, t.col - hstep, accurate, nullptr);
-  const unsigned right = check_better(sp, t.row, t.col + hstep, accurate, nullptr);
-  const unsigned up = check_better(sp, t.row - hstep, t.col, accurate, nullptr);
-  const unsigned down = check_better(sp, t.row + hstep, t.col, accurate, nullptr);
+  unsigned left, right, up, down;
+  // The batched pass pays off for the throughput-bound 16x16 searches; the latency-bound 32x32 search
+  // is faster with four short passes than with one pass of four times the dependent work per lane.
+  if (accurate || W == 32) {
+    left = check_better(sp, t.row, t.col - hstep, accurate, nullptr);
+    right = check_better(sp, t.row, t.col + hstep, accurate, nullptr);
+    up = check_better(sp, t.row - hstep, t.col, accurate, nullptr);
+    down = check_better(sp, t.row + hstep, t.col, accurate, nullptr);
+  } else {
+    // one pass for the four candidates, then check_better's comparisons in the reference's order
+    const unsigned vm = (in_range(sp.lim, t.row, t.col - hstep) ? 1u : 0u) | (in_range(sp.lim, t.row, t.col + hstep) ? 2u : 0u) |
+                        (in_range(sp.lim, t.row - hstep, t.col) ? 4u : 0u) | (in_range(sp.lim, t.row + hstep, t.col) ? 8u : 0u);
+    const uint4 c = bilinear_err4<T, W>(*sp.S, t.row, t.col, hstep, vm);
+    left = c.x, right = c.y, up = c.z, down = c.w;
+    const int dr[4] = { 0, 0, -hstep, hstep }, dc[4] = { -hstep, hstep, 0, 0 };
+    const unsigned cs[4] = { left, right, up, down };
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (cs[i] < sp.besterr) {  // invalid candidates carry INT_MAX and never win
+        sp.besterr = cs[i];
+        sp.best.row = t.row + dr[i];
+        sp.best.col = t.col + dc[i];
+      }
+  }
   MV2 diag;
   diag.row = up <= down ? -hstep : hstep;
   diag.col = left <= right ? -hstep : hstep;
