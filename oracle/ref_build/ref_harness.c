@@ -388,6 +388,12 @@ static void tfref_setup_tf_ctx(tfref_ctx *t) {
 /* Runs the reference-side CONFIG_TF_GPU seam (integration/tf_gpu_seam.patch): the exact
  * code a maintainer adds to av1_temporal_filter(), filling tf_gpu_params / tf_gpu_frame
  * from AV1_COMP and calling libtf_gpu.so. */
+/* The patch's replacement for the noise-estimation loop of tf_setup_filtering_buffer(). */
+TFREF_API void tfref_gpu_noise_levels(void *h, int idx, double *noise_levels) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  tf_gpu_noise_levels(t->cpi, &t->frames[idx].entry, noise_levels);
+}
+
 TFREF_API void tfref_run_gpu_seam(void *h, int64_t *diff_sum_sse) {
   tfref_ctx *t = (tfref_ctx *)h;
   tfref_setup_tf_ctx(t);

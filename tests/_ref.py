@@ -66,6 +66,7 @@ def seam_lib():
     if _seam is None:
         _seam = _bind(C.CDLL(SEAM_LIB))
         _seam.tfref_run_gpu_seam.argtypes = [C.c_void_p, C.c_void_p]
+        _seam.tfref_gpu_noise_levels.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     return _seam
 
 
@@ -163,6 +164,13 @@ class RefFilter:
             self.L.tfref_get_output(self.h, pl, _ptr(o), w, h)
             out.append(o)
         return out
+
+    def gpu_noise_levels(self, idx=None):
+        """The CONFIG_TF_GPU replacement of the noise loop in tf_setup_filtering_buffer()."""
+        idx = self.p["filter_frame_idx"] if idx is None else idx
+        out = (C.c_double * 3)(0.0, 0.0, 0.0)
+        self.L.tfref_gpu_noise_levels(self.h, idx, out)
+        return [out[i] for i in range(self.num_planes)]
 
     def run_gpu_seam(self):
         """av1_temporal_filter()'s CONFIG_TF_GPU branch: the reference-side shim calls libtf_gpu.so."""

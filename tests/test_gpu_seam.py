@@ -45,3 +45,16 @@ def test_reference_side_shim_matches_reference_cpu_path(case):
     assert (a["diff"] == b["diff"]).all()
     cpu.close()
     seam.close()
+
+
+@pytest.mark.parametrize("case", CASES[:5], ids=[c[0] for c in CASES[:5]])
+def test_reference_side_noise_hunk_matches_reference(case):
+    """The patch's second hunk: tf_setup_filtering_buffer() takes its noise levels from
+    tf_gpu_estimate_noise(); they must be the doubles av1_estimate_noise_from_single_plane() returns."""
+    name, W, H, N, bd, pkw = case
+    frames = _clips.moving_texture(W, H, N, bd, ss_x=pkw.get("ss_x", 1), ss_y=pkw.get("ss_y", 1))
+    p = _params.tf_params(W, H, N, bit_depth=bd, **pkw)
+    seam = _ref.RefFilter(p, frames, seam=True)
+    want = _ref.RefFilter(p, frames).estimate_noise()
+    assert seam.gpu_noise_levels() == want
+    seam.close()

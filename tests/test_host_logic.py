@@ -1,4 +1,6 @@
 """CPU: host-side logic -- parameter presets, YV12 layout mirror, clip generator, sharding."""
+import os
+
 import numpy as np
 import pytest
 
@@ -64,3 +66,23 @@ def test_int_roofline_work_matches_survey():
     w = bench.int_work_per_block_ref(allow_hp=1)
     assert w["sad"] == 144384 and w["var"] == 4096 and w["pred"] == 53760 and w["weights"] == 44544
     assert w["subpel"] == 16 * 2048 * 6
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/av1/encoder/temporal_filter.c"),
+                    reason="reference tree not present (GPU box)")
+def test_seam_patch_applies_to_the_reference(tmp_path):
+    """integration/tf_gpu_seam.patch is a well-formed unified diff against the reference tree."""
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    patch = os.path.join(root, "integration", "tf_gpu_seam.patch")
+    files = re.findall(r"^--- a/(\S+)$", open(patch).read(), re.M)
+    assert sorted(files) == ["CMakeLists.txt", "av1/encoder/temporal_filter.c", "build/cmake/aom_config_defaults.cmake"]
+    for rel in files:
+        os.makedirs(os.path.dirname(tmp_path / rel), exist_ok=True)
+        shutil.copyfile(os.path.join("/root/reference", rel), tmp_path / rel)
+    r = subprocess.run(["patch", "-p1", "-s", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    patched = open(tmp_path / "av1/encoder/temporal_filter.c").read()
+    assert "tf_gpu_do_filtering(cpi, frame_diff);" in patched and "tf_gpu_noise_levels(cpi, to_filter_buf, noise_levels);" in patched
