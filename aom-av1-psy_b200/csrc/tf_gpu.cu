@@ -121,6 +121,13 @@ int fail(tf_gpu_ctx *c, int code, const char *fmt, ...) {
 
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
+// Grid of a grid-stride kernel over n items: enough blocks for the items, at most `per_sm` per SM, at least one.
+int grid_for(const tf_gpu_ctx *ctx, long long n, int threads, int per_sm) {
+  long long b = (n + threads - 1) / threads;
+  if (b > (long long)ctx->num_sms * per_sm) b = (long long)ctx->num_sms * per_sm;
+  return b < 1 ? 1 : (int)b;
+}
+
 // Takes a new epoch for an entry point and records that epoch's completion event on the way out
 // (also on error paths, so done_ev[e & 1] never refers to a call older than e - 2).
 struct CallScope {
@@ -185,7 +192,7 @@ int upload_frame(tf_gpu_ctx *ctx, DevFrame *d, const tf_gpu_frame *f) {
     const int ext_w = g.aligned_w[k] + g.bx[k], ext_h = g.aligned_h[k] + g.by[k];
     const long long n = (long long)g.crop_h[k] * (g.bx[k] + ext_w - g.crop_w[k]) + (long long)(g.by[k] + ext_h - g.crop_h[k]) * (g.bx[k] + ext_w);
     const int threads = 256;
-    const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads < 1 ? 1 : (n + threads - 1) / threads);
+    const int blocks = grid_for(ctx, n, threads, 16);
     if (g.is_hbd)
       extend_borders_kernel<uint16_t><<<blocks, threads, 0, ctx->copy_stream>>>((uint16_t *)d->p00[p], g.pitch[k],
                                                                           g.crop_w[k], g.crop_h[k], g.bx[k], g.by[k],
@@ -558,7 +565,7 @@ int extend_and_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, cudaStream_t 
     const int ext_w = g.aligned_w[k] + hb_x, ext_h = g.aligned_h[k] + hb_y;  // right / bottom extents from pixel 0
     const long long n = (long long)g.crop_h[k] * (hb_x + ext_w - g.crop_w[k]) + (long long)(hb_y + ext_h - g.crop_h[k]) * (hb_x + ext_w);
     const int threads = 256;
-    const int blocks = (int)((n + threads - 1) / threads > 148 * 16 ? 148 * 16 : (n + threads - 1) / threads < 1 ? 1 : (n + threads - 1) / threads);
+    const int blocks = grid_for(ctx, n, threads, 16);
     if (!out->plane[pl]) return fail(ctx, TF_GPU_ERR_INVALID, "output plane %d is NULL", pl);
     if (g.is_hbd)
       extend_borders_kernel<uint16_t><<<blocks, threads, 0, ctx->stream>>>((uint16_t *)ctx->out.p00[pl], g.pitch[k], g.crop_w[k], g.crop_h[k], hb_x, hb_y, ext_w, ext_h);
@@ -826,7 +833,7 @@ int tf_gpu_estimate_noise(tf_gpu_ctx *ctx, const tf_gpu_frame *frame, int plane,
     const long long n = (long long)(w - 2) * (h - 2);
     const int threads = 256;
     long long blocks = (n + threads - 1) / threads;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
     if (g.is_hbd)
       noise_kernel<uint16_t><<<(int)blocks, threads, 0, ctx->stream>>>((const uint16_t *)d->p00[plane], g.pitch[k], w, h, bit_depth, edge_thresh, ctx->d_noise);
     else
