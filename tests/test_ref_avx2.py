@@ -38,3 +38,22 @@ def test_avx2_flavour_matches_generic_c(w, h, bd, n, speed, extra):
     assert np.array_equal(a["pred"], b["pred"])
     for x, y in zip(a["out"], b["out"]):
         assert np.abs(x.astype(np.int32) - y.astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("TF_FUZZ_SEEDS", "30"))))
+def test_avx2_flavour_matches_generic_c_random_configurations(seed):
+    """Same seeded sweep as tests/test_gpu_fuzz.py (sizes, formats, bit depths, speed classes)."""
+    from test_gpu_fuzz import _case
+    W, H, N, bd, kw, clip, random_frames = _case(seed)
+    fk = dict(ss_x=kw["ss_x"], ss_y=kw["ss_y"], monochrome=kw["monochrome"])
+    frames = (_clips.random_frames(W, H, N, bd, seed=clip["seed"], **fk) if random_frames
+              else _clips.moving_texture(W, H, N, bd, **fk, **clip))
+    p = _params.tf_params(W, H, N, bit_depth=bd, **kw)
+    ra, rb = _ref.RefFilter(p, frames), _ref.RefFilter(p, frames, avx2=True)
+    a, b = ra.run(), rb.run()
+    assert np.array_equal(a["mvs"], b["mvs"]) and np.array_equal(a["mses"], b["mses"])
+    assert np.array_equal(a["pred"], b["pred"])
+    for x, y in zip(a["out"], b["out"]):
+        assert np.abs(x.astype(np.int32) - y.astype(np.int32)).max() <= 1
+    ra.close()
+    rb.close()
