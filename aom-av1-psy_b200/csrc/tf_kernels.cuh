@@ -794,20 +794,18 @@ __device__ __noinline__ int full_pixel_search_pass(Search<T> &S, const KParams &
     if (d <= thr) run_mesh = 0;
   }
   if (SKIP) {
-    // sdf and sdsf at best_mv, column-wise (two evaluations per search)
+    // sdf and sdsf at best_mv: one full-row SAD pass (one block row per lane, the window when best_mv lies
+    // inside it); the skip-row SAD is the sum over the even rows of the same pass
+    using LF = SadL<T, W, false>;
     const int lane = lane_id();
-    constexpr int RP = 32 / W;
-    const int col = lane % W, r0 = lane / W;
-    const T *a = S.src, *b = S.ref + best_mv->row * S.stride + best_mv->col;
-    unsigned s_all = 0, s_even = 0;
-#pragma unroll 4
-    for (int i = r0; i < W; i += RP) {
-      const unsigned d = (unsigned)iabs((int)__ldg(a + i * S.stride + col) - (int)__ldg(b + i * S.stride + col));
-      s_all += d;
-      if ((i & 1) == 0) s_even += d;
-    }
-    s_all = seg_reduce_u32<32>(s_all);
-    s_even = seg_reduce_u32<32>(s_even);
+    const int row = lane % LF::LPC;
+    uint32_t swf[LF::NW];
+    sad_load_src<T, W, false>(S.src, S.stride, swf);
+    const SadSrc Q = sad_src(S, window_covers(S, best_mv->row, best_mv->col, 0));
+    const unsigned part = sad_partial<T, W, false>(Q, reinterpret_cast<const unsigned char *>(S.src), best_mv->row,
+                                                   best_mv->col, row, true, swf);
+    const unsigned s_all = seg_reduce_u32<LF::LPC>(part);
+    const unsigned s_even = seg_reduce_u32<LF::LPC>((row & 1) ? 0u : part);
     const int sad = (int)(s_all >> S.hbd_shift);
     const int skip_sad = (int)((2 * s_even) >> S.hbd_shift);
     const int kSADThresh = W * W / 16;
