@@ -94,8 +94,8 @@ struct tf_gpu_ctx {
   int last_launches = 0;
   float last_kernel_ms = 0.f;
   // dump buffers (device), grown on demand
-  void *d_dump[12] = {};
-  size_t d_dump_sz[12] = {};
+  void *d_dump[10] = {};
+  size_t d_dump_sz[10] = {};
   char err[512] = { 0 };
 };
 
@@ -451,16 +451,10 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     rc = ensure_dump(ctx, 9, (size_t)nblocks_all * 2 * sizeof(int16_t));
     if (rc) return rc;
     K.s_ref_mv = (int16_t *)ctx->d_dump[9];
-    rc = ensure_dump(ctx, 10, bf * MEMO_K * sizeof(int32_t));
-    if (rc) return rc;
-    rc = ensure_dump(ctx, 11, bf * MEMO_K * 4 * sizeof(unsigned long long));
-    if (rc) return rc;
-    K.s_memo_mv = (int32_t *)ctx->d_dump[10];
-    K.s_memo_q = (unsigned long long *)ctx->d_dump[11];
   }
   const int grid = (K.row_end - K.row_begin) * K.mb_cols;
   if (grid <= 0) return fail(ctx, TF_GPU_ERR_INVALID, "empty row range");
-  const size_t smem_search = WIN_BYTES + MEMO_SMEM;
+  const size_t smem_search = WIN_BYTES;
   const size_t smem_filter = filter_smem_bytes(K.num_pels);
   const int nref = p->num_frames - 1;
   // the frame to filter is read by every kernel
@@ -496,8 +490,8 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
         KParams K16 = Kf;
         // task decode expects [frame_begin, frame_end) minus the centre: a single non-centre frame
         K16.filter_idx = K.filter_idx;
-        if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4, 32, WIN16_BYTES + MEMO_SMEM, ctx->stream2>>>(K16);
-        else tf_search16_kernel<uint8_t><<<grid * 4, 32, WIN16_BYTES + MEMO_SMEM, ctx->stream2>>>(K16);
+        if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4, 32, WIN16_BYTES, ctx->stream2>>>(K16);
+        else tf_search16_kernel<uint8_t><<<grid * 4, 32, WIN16_BYTES, ctx->stream2>>>(K16);
         nlaunch++;
         any16 = true;
       }
@@ -770,7 +764,7 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
   if (ctx->ev_out_done) cudaEventDestroy(ctx->ev_out_done);
   for (int p = 0; p < 3; p++)
     if (ctx->out.base[p]) cudaFree(ctx->out.base[p]);
-  for (int i = 0; i < 12; i++)
+  for (int i = 0; i < 10; i++)
     if (ctx->d_dump[i]) cudaFree(ctx->d_dump[i]);
   if (ctx->d_diff) cudaFree(ctx->d_diff);
   if (ctx->h_diff) cudaFreeHost(ctx->h_diff);

@@ -79,9 +79,6 @@ struct KParams {
   int32_t *s_blk_mse;
   int16_t *s_sub_mv;   // 16x16 results
   int32_t *s_sub_mse;
-  // quadrant-statistics memo handed from the 32x32 search to the 16x16 searches (see Memo below)
-  int32_t *s_memo_mv;             // [blocks][num_frames][MEMO_K] keys
-  unsigned long long *s_memo_q;   // [blocks][num_frames][MEMO_K][4] packed (sse, sum) per 16x16 quadrant
   int num_pels;
 };
 
@@ -143,55 +140,7 @@ struct Search {
   // optional executed-work counters (bench instrumentation; nullptr in normal runs):
   // [0] SAD sample pairs read, [1] sub-pel candidate evaluations x block samples, [2] variance samples
   unsigned long long *ctr;
-  // Error memo (see "Quadrant-statistics memo"): warp-private shared memory, nullptr = off.
-  uint32_t *memo;
-  // producer side (32x32 search): this (block, frame)'s global memo rows; nullptr in the 16x16 searches
-  int32_t *memo_mv_g;
-  unsigned long long *memo_q_g;
 };
-
-// ---------------------------------------------------------------------------
-// Quadrant-statistics memo.  The sub-pel error and the full-pel variance are
-// pure functions of (block, MV): (sum, sse) of predictor - source.  The four
-// 16x16 sub-blocks tile the 32x32 block and share its MV limits
-// (temporal_filter.c:202-205), and a 16x16 candidate's predictor is the
-// matching quadrant of the 32x32 candidate's predictor at the same MV.  In the
-// 32x32 evaluation every lane works inside one quadrant (lane >> 3), so the
-// quadrant totals fall out of the first three steps of the warp reduction: the
-// 32x32 search stores them per evaluated MV, and a 16x16 search that reaches
-// the same MV (it starts from the 32x32 result, so on coherent motion nearly
-// all of its sub-pel candidates) takes the statistics from the memo instead of
-// filtering the block again.  Bit-exact: the same integers enter var_finish.
-// Layout in shared memory (warp-private): [0] n, [1..MEMO_K] keys
-// (r8 << 16 | c8 & 0xffff), then u64 stats[MEMO_K] = sse << 24 | (sum + 2^22).
-// ---------------------------------------------------------------------------
-constexpr int MEMO_K = 24;
-constexpr int MEMO_INVALID = (int)0x80000000;
-constexpr int MEMO_STATS_OFF = 104;                       // bytes: (1 + MEMO_K) * 4 rounded up to 8
-constexpr int MEMO_BYTES = MEMO_STATS_OFF + MEMO_K * 8;   // 296
-constexpr int MEMO_SMEM = 304;                            // rounded to 16
-__device__ __forceinline__ int memo_key(int r8, int c8) { return (r8 << 16) | (c8 & 0xffff); }
-__device__ __forceinline__ unsigned long long *memo_stats(uint32_t *memo) {
-  return reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(memo) + MEMO_STATS_OFF);
-}
-// Index of `key` in the memo or -1 (warp-uniform).
-__device__ __forceinline__ int memo_find(const uint32_t *memo, int key, int lane) {
-  const int n = (int)memo[0];
-  const bool hit = lane < n && (int)memo[1 + lane] == key;
-  const unsigned m = __ballot_sync(FULL, hit);
-  return m ? __ffs(m) - 1 : -1;
-}
-// Appends an entry (packed totals with the 2^22 sum offset); no-op when full.
-__device__ __forceinline__ void memo_append(uint32_t *memo, int key, unsigned long long pk, int lane) {
-  const int n = (int)memo[0];
-  __syncwarp();
-  if (n < MEMO_K && lane == 0) {
-    memo[1 + n] = (uint32_t)key;
-    memo_stats(memo)[n] = pk;
-    memo[0] = (uint32_t)(n + 1);
-  }
-  __syncwarp();
-}
 
 #ifndef TF_VAR_VIA_SUBPEL
 #define TF_VAR_VIA_SUBPEL 1
@@ -904,17 +853,6 @@ template <typename T, int W>
 __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int mode) {
   const Search<T> S = S_in;
   const int lane = lane_id();
-  const int key = memo_key(r8, c8);
-  if (S.memo) {  // already evaluated at this MV (by this search or, for a 16x16 search, by the 32x32 one)
-    const int idx = memo_find(S.memo, key, lane);
-    if (idx >= 0) {
-      const unsigned long long pk = memo_stats(S.memo)[idx];
-      int sum = (int)(pk & 0xffffffu) - (1 << 22);
-      if (mode == 3) sum = -sum;
-      unsigned sse_out;
-      return var_finish(sum, pk >> 24, W, S.hbd_shift, &sse_out);
-    }
-  }
   const int fr = r8 >> 3, fc = c8 >> 3;
   const int xo = c8 & 7, yo = r8 & 7;
   // Two samples per 32-bit register (16-bit halves; 8-bit samples are widened on load).  The taps
@@ -984,28 +922,10 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
     }
   }
   if (S.ctr && lane == 0) atomicAdd(&S.ctr[mode == 1 ? 1 : 2], (unsigned long long)(W * W));
-  // (sum, sse) of predictor - source, packed for one 64-bit reduction: |sum| < 2^17 per lane, so
-  // sum + 2^17 is non-negative and 32 of them stay below 2^23; sse totals < 2^35
-  unsigned long long pk =
-      ((unsigned long long)(accl + (acch << 8)) << 24) | (unsigned)((int)sumv - (int)sums + (1 << 17));
-#pragma unroll
-  for (int o = 1; o <= 4; o <<= 1) pk += __shfl_xor_sync(FULL, pk, o);
-  if (W == 32 && S.memo_q_g) {
-    // lanes 8q .. 8q+7 cover quadrant q (row band = lane / 16, column half = (lane / 8) & 1): after
-    // three steps every lane holds its quadrant's totals -> the memo for the 16x16 searches
-    const int n = (int)S.memo[0];
-    if (n < MEMO_K) {
-      if ((lane & 7) == 0) S.memo_q_g[n * 4 + (lane >> 3)] = pk + ((1ull << 22) - (1ull << 20));
-      if (lane == 0) S.memo_mv_g[n] = key;
-    }
-  }
-  pk += __shfl_xor_sync(FULL, pk, 8);
-  pk += __shfl_xor_sync(FULL, pk, 16);
-  if (S.memo) memo_append(S.memo, key, pk, lane);
-  int sum = (int)(pk & 0xffffffu) - (1 << 22);
-  if (mode == 3) sum = -sum;
+  int sum = mode == 3 ? (int)sums - (int)sumv : (int)sumv - (int)sums;
+  const unsigned long long sse64 = warp_sum_pair(sum, accl + (acch << 8));
   unsigned sse_out;
-  return var_finish(sum, pk >> 24, W, S.hbd_shift, &sse_out);
+  return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
 }
 
 // The four first-level candidates of a sub-pel round (left, right, up, down of (tr, tc) at distance
@@ -1022,30 +942,6 @@ __device__ __noinline__ uint4 bilinear_err4(const Search<T> &S_in, int tr, int t
   constexpr int NP = W / 16;            // column pairs per lane
   constexpr int CH = NP == 1 ? 8 : 4;   // rows per chunk: all loads of a chunk are issued before use
   const int lane = lane_id(), g = lane >> 3, u = lane & 7;
-  int midx[4] = { -1, -1, -1, -1 };
-  if (S.memo) {  // all four in the memo (the 32x32 search evaluated the same round): nothing to filter
-    bool all = true;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (!((validmask >> i) & 1u)) continue;
-      const int kr = tr + (i == 2 ? -hstep : (i == 3 ? hstep : 0)), kc = tc + (i == 0 ? -hstep : (i == 1 ? hstep : 0));
-      midx[i] = memo_find(S.memo, memo_key(kr, kc), lane);
-      all = all && midx[i] >= 0;
-    }
-    if (all) {
-      unsigned c[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        c[i] = (unsigned)INT_MAX_;
-        if (midx[i] >= 0) {
-          const unsigned long long pk = memo_stats(S.memo)[midx[i]];
-          unsigned sse_out;
-          c[i] = var_finish((int)(pk & 0xffffffu) - (1 << 22), pk >> 24, W, S.hbd_shift, &sse_out);
-        }
-      }
-      return make_uint4(c[0], c[1], c[2], c[3]);
-    }
-  }
   const bool valid = (validmask >> g) & 1u;
   int r8 = tr, c8 = tc;
   if (valid) {
@@ -1124,16 +1020,6 @@ __device__ __noinline__ uint4 bilinear_err4(const Search<T> &S_in, int tr, int t
   unsigned long long pk = ((unsigned long long)(accl + (acch << 8)) << 24) | (unsigned)((int)sumv - (int)sums + (1 << 19));
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1) pk += __shfl_xor_sync(FULL, pk, o);
-  if (S.memo) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const unsigned long long pki = __shfl_sync(FULL, pk, 8 * i);
-      if (((validmask >> i) & 1u) && midx[i] < 0) {
-        const int kr = tr + (i == 2 ? -hstep : (i == 3 ? hstep : 0)), kc = tc + (i == 0 ? -hstep : (i == 1 ? hstep : 0));
-        memo_append(S.memo, memo_key(kr, kc), pki, lane);
-      }
-    }
-  }
   const int sum = (int)(pk & 0xffffffu) - (1 << 22);
   unsigned sse_out;
   const unsigned mine = valid ? var_finish(sum, pk >> 24, W, S.hbd_shift, &sse_out) : (unsigned)INT_MAX_;
@@ -1364,9 +1250,6 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
   S.win = nullptr;
   S.wr = S.wc = S.wR = S.wpitch = S.wshift = 0;
   S.ctr = P.ctr;
-  S.memo = nullptr;
-  S.memo_mv_g = nullptr;
-  S.memo_q_g = nullptr;
   // av1_set_mv_{row,col}_limits (mcomp.h:216-240) + av1_set_mv_search_range (mcomp.c:196-215)
   const int border = P.border, mi_row = mb_row * 8, mi_col = mb_col * 8;
   S.lim.row_min = imax(-(mi_row * 4 + border - 8), -(((mi_row + 8) * 4) + 8));
@@ -1412,12 +1295,6 @@ __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_cons
       continue;
     }
     S.ref = reinterpret_cast<const T *>(P.frm[frame][0]) + y_offset;
-    const size_t bf = (size_t)blk * P.num_frames + frame;
-    S.memo = reinterpret_cast<uint32_t *>(smem_raw + WIN_BYTES);
-    S.memo_mv_g = P.s_memo_mv + bf * MEMO_K;
-    S.memo_q_g = P.s_memo_q + bf * MEMO_K * 4;
-    if (lane == 0) S.memo[0] = 0;
-    __syncwarp();
     const MV2 start = { rawpel(ref_mv.row), rawpel(ref_mv.col) };
     MV2 best_full;
     full_pixel_search<T, 32>(S, P, start, &best_full, smem_raw);
@@ -1435,11 +1312,8 @@ __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_cons
       block_mse = (int)((err + 512u) / 1024u);
       ref_mv = block_mv;
     }
-    {  // close the memo of this (block, frame): the unused keys are marked invalid
-      const int n = (int)S.memo[0];
-      if (lane >= n && lane < MEMO_K) S.memo_mv_g[lane] = MEMO_INVALID;
-    }
     if (lane == 0) {
+      const size_t bf = (size_t)blk * P.num_frames + frame;
       P.s_blk_mv[bf * 2 + 0] = (int16_t)block_mv.row;
       P.s_blk_mv[bf * 2 + 1] = (int16_t)block_mv.col;
       P.s_blk_mse[bf] = block_mse;
@@ -1482,20 +1356,6 @@ __global__ void __launch_bounds__(32, 24) tf_search16_kernel(const __grid_consta
   S.ref = reinterpret_cast<const T *>(P.frm[frame][0]) + off;
   const size_t bf = (size_t)blk * P.num_frames + frame;
   const MV2 start = { rawpel((int)P.s_blk_mv[bf * 2 + 0]), rawpel((int)P.s_blk_mv[bf * 2 + 1]) };
-  {  // this sub-block's quadrant statistics of every MV the 32x32 search evaluated
-    uint32_t *memo = reinterpret_cast<uint32_t *>(smem_raw + WIN16_BYTES);
-    const int key = lane < MEMO_K ? P.s_memo_mv[bf * MEMO_K + lane] : MEMO_INVALID;
-    const bool ok = key != MEMO_INVALID;
-    const unsigned long long q = ok ? P.s_memo_q[(bf * MEMO_K + lane) * 4 + sub] : 0ull;
-    const int n = __popc(__ballot_sync(FULL, ok));  // the producer fills a prefix
-    if (lane < MEMO_K) {
-      memo[1 + lane] = (uint32_t)key;
-      memo_stats(memo)[lane] = q;
-    }
-    if (lane == 0) memo[0] = (uint32_t)n;
-    __syncwarp();
-    S.memo = memo;
-  }
   MV2 best_full, best;
   full_pixel_search<T, 16>(S, P, start, &best_full, smem_raw);
   const unsigned err = subpel_search<T, 16>(S, P, best_full, &best, reinterpret_cast<T *>(smem_raw));
