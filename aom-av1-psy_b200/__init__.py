@@ -31,6 +31,7 @@ EXPORTS = [
     "tf_gpu_evict_frame", "tf_gpu_filter_resident", "tf_gpu_download_output", "tf_gpu_output_device_plane",
     "tf_gpu_host_register", "tf_gpu_host_unregister", "tf_gpu_last_stats", "tf_gpu_event_record",
     "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench", "tf_gpu_last_kernel_times", "tf_gpu_filter_resident_async", "tf_gpu_filter_resident_result", "tf_gpu_collect_counters", "tf_gpu_read_counters",
+    "tf_gpu_cache_frame_async", "tf_gpu_debug_read_plane", "tf_gpu_device_border",
 ]
 
 
@@ -62,7 +63,8 @@ class Params(C.Structure):
         ("allow_hp", C.c_int), ("subpel_method", C.c_int), ("subpel_iters_per_step", C.c_int),
         ("prune_mesh_level", C.c_int), ("mesh_patterns", (C.c_int * 2) * 4), ("use_downsampled_sad", C.c_int),
         ("compute_frame_diff", C.c_int), ("out_row_begin", C.c_int), ("out_row_end", C.c_int),
-        ("extend_output_borders", C.c_int), ("reserved", C.c_int * 7),
+        ("extend_output_borders", C.c_int), ("cm_width", C.c_int), ("cm_height", C.c_int),
+        ("reserved", C.c_int * 5),
     ]
 
 
@@ -96,6 +98,9 @@ def load_library():
     lib.tf_gpu_wait.argtypes = [vp, u64]
     lib.tf_gpu_cache_frame.argtypes = [vp, C.POINTER(Frame)]
     lib.tf_gpu_evict_frame.argtypes = [vp, u64]
+    lib.tf_gpu_cache_frame_async.argtypes = [vp, C.POINTER(Frame)]
+    lib.tf_gpu_debug_read_plane.argtypes = [vp, u64, i, vp, i, i, i, i, i]
+    lib.tf_gpu_device_border.restype = i
     lib.tf_gpu_filter_resident.argtypes = [vp, C.POINTER(Params), C.POINTER(u64), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_float)]
     lib.tf_gpu_download_output.argtypes = [vp, C.POINTER(Frame), i, i]
@@ -213,6 +218,7 @@ def make_params(p):
     c.use_downsampled_sad, c.compute_frame_diff = p["use_downsampled_sad"], p["compute_frame_diff"]
     c.out_row_begin, c.out_row_end = p.get("out_row_begin", 0), p.get("out_row_end", 0)
     c.extend_output_borders = p.get("extend_output_borders", 0)
+    c.cm_width, c.cm_height = p.get("cm_width", 0), p.get("cm_height", 0)
     return c
 
 
@@ -291,6 +297,20 @@ class TemporalFilterGpu:
     def cache_frame(self, frame):
         cf = frame.c_frame()
         self._check(self.lib.tf_gpu_cache_frame(self.h, C.byref(cf)))
+
+    def cache_frame_async(self, frame):
+        """Upload without waiting (at most one outstanding; see tf_gpu.h)."""
+        cf = frame.c_frame()
+        self._check(self.lib.tf_gpu_cache_frame_async(self.h, C.byref(cf)))
+
+    def debug_read_plane(self, frame, plane, x0, y0, w, h):
+        """Rectangle of a cached device plane, border included (test hook for the upload path)."""
+        dst = np.zeros((h, w), frame.dtype)
+        self._check(self.lib.tf_gpu_debug_read_plane(self.h, frame.frame_id, plane, dst.ctypes.data, w, x0, y0, w, h))
+        return dst
+
+    def device_border(self):
+        return self.lib.tf_gpu_device_border()
 
     def evict_frame(self, frame_id):
         self._check(self.lib.tf_gpu_evict_frame(self.h, frame_id))

@@ -46,9 +46,17 @@ struct DevFrame {
   cudaEvent_t ready = nullptr;                    // upload + border extension finished (copy stream)
 };
 
+// Timing events of one filter call (main stream): start, after the search32 chain, after the
+// search16 join, end.  One set per ticket and one for the resident path, so pipelined submits never
+// read each other's times.
+struct CallEvents {
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk[2] = { nullptr, nullptr };
+};
+
 struct Ticket {
   uint64_t id = 0;
   cudaEvent_t ev = nullptr;
+  CallEvents te;
   int64_t *diff_dst = nullptr;
   bool want_diff = false;
   bool pending = false;
@@ -74,15 +82,18 @@ struct tf_gpu_ctx {
   bool done_valid[2] = { false, false };
   cudaEvent_t ev_f32[TF_GPU_MAX_FRAMES] = {};
   cudaEvent_t ev_s16 = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t evk[2] = { nullptr, nullptr };  // after search32, after search16
-  float last_kernel_split[3] = { 0.f, 0.f, 0.f };
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // microbenchmark timing
+  CallEvents res_ev;                          // resident path
+  const CallEvents *last_ev = nullptr;        // events of the last completed filter call
   bool split_valid = false;
+  cudaStream_t noise_stream = nullptr;        // noise estimates do not queue behind a submitted window
+  cudaEvent_t ev_async_upload = nullptr;      // last tf_gpu_cache_frame_async upload
+  bool async_upload_pending = false;
   cudaEvent_t user_ev[4] = { nullptr, nullptr, nullptr, nullptr };
   std::vector<DevFrame> cache;
   DevFrame out;
   uint64_t use_counter = 0, epoch = 0;
-  unsigned long long *d_diff = nullptr;   // [8][2] ring
+  unsigned long long *d_diff = nullptr;   // [9][2]: one slot per ticket, slot 8 = resident path
   unsigned long long *h_diff = nullptr;   // pinned mirror
   unsigned long long *d_noise = nullptr;  // [2]
   unsigned long long *d_ctr = nullptr;    // [4] executed-work counters (instrumentation)
@@ -274,6 +285,28 @@ int validate_params(tf_gpu_ctx *ctx, const tf_gpu_params *p) {
   if (p->subpel_method < 0 || p->subpel_method > 2) return fail(ctx, TF_GPU_ERR_INVALID, "bad subpel_method");
   if (p->filter_strength < 0 || p->filter_strength > 6) return fail(ctx, TF_GPU_ERR_INVALID, "filter_strength out of [0,6]");
   if (p->q_factor < 0 || p->q_factor > 255 * 8) return fail(ctx, TF_GPU_ERR_INVALID, "q_factor out of range");
+  if (p->subpel_iters_per_step < 1 || p->subpel_iters_per_step > 2) return fail(ctx, TF_GPU_ERR_INVALID, "subpel_iters_per_step must be 1 or 2");
+  if (p->prune_mesh_level < 0 || p->prune_mesh_level > 2) return fail(ctx, TF_GPU_ERR_INVALID, "bad prune_mesh_level");
+  for (int i = 0; i < 4; i++)
+    if (p->mesh_patterns[i][0] < 0 || p->mesh_patterns[i][0] > 256 || p->mesh_patterns[i][1] < 0 || p->mesh_patterns[i][1] > 256)
+      return fail(ctx, TF_GPU_ERR_INVALID, "mesh pattern %d out of [0,256]", i);
+  // the smallest border the encoder configures is 64 (AOM_ENC_ALLINTRA_BORDER); below 40 the MV limits
+  // of av1_set_mv_{row,col}_limits (mcomp.h:216-240) can invert
+  if (p->border_in_pixels < 40 || p->border_in_pixels > 1024) return fail(ctx, TF_GPU_ERR_INVALID, "border_in_pixels out of [40,1024]");
+  if (p->cm_width < 0 || p->cm_height < 0) return fail(ctx, TF_GPU_ERR_INVALID, "negative cm_width / cm_height");
+  return TF_GPU_OK;
+}
+
+// Parameters against the geometry of the window: the device MV limits come from mi_rows / mi_cols while
+// the device planes are sized from the frames' aligned size plus DEV_BORDER, so a caller whose mi grid
+// exceeds the frames would make the search read outside the allocation.
+int validate_geometry(tf_gpu_ctx *ctx, const tf_gpu_params *p, const Geometry &g) {
+  if (p->mi_rows <= 0 || p->mi_cols <= 0) return fail(ctx, TF_GPU_ERR_INVALID, "mi_rows / mi_cols must be positive");
+  if (p->mi_rows * 4 > g.aligned_h[0] || p->mi_cols * 4 > g.aligned_w[0])
+    return fail(ctx, TF_GPU_ERR_INVALID, "mi grid %dx%d exceeds the frame's aligned size %dx%d", p->mi_cols * 4, p->mi_rows * 4,
+                g.aligned_w[0], g.aligned_h[0]);
+  if (g.is_hbd == 0 && p->bit_depth != 8) return fail(ctx, TF_GPU_ERR_INVALID, "8-bit container needs bit_depth 8");
+  if (g.num_planes < p->num_planes) return fail(ctx, TF_GPU_ERR_INVALID, "frames lack chroma planes");
   return TF_GPU_OK;
 }
 
@@ -345,7 +378,8 @@ int ensure_dump(tf_gpu_ctx *ctx, int i, size_t bytes) {
 
 // Build kernel parameters and launch the block kernel over rows [rb, re).
 int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *frames, const Geometry &g,
-                  unsigned long long *d_diff, const tf_gpu_dump *dump, bool timed) {
+                  unsigned long long *d_diff, const tf_gpu_dump *dump, const CallEvents *te) {
+  const bool timed = te != nullptr;
   KParams K;
   memset(&K, 0, sizeof(K));
   K.width = g.crop_w[0];
@@ -381,10 +415,13 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   }
   K.use_skip = p->use_downsampled_sad ? 1 : 0;
   K.compute_diff = p->compute_frame_diff ? 1 : 0;
-  const int min_frame_size = K.width < K.height ? K.width : K.height;
+  const int min_frame_size = K.width < K.height ? K.width : K.height;  // av1_apply_temporal_filter_c: the source size (:603)
+  // tf_motion_search() uses cm->width / cm->height (the coded size; temporal_filter.c:99-100)
+  const int cm_w = p->cm_width > 0 ? p->cm_width : K.width, cm_h = p->cm_height > 0 ? p->cm_height : K.height;
+  const int min_cm_size = cm_w < cm_h ? cm_w : cm_h;
   // MV_COST_L1_{LOW,MID,HD}RES (temporal_filter.c:119-122, mcomp.c:237-244)
-  if (min_frame_size >= 720) { K.sad_lambda = 8; K.sse_lambda = 1; }
-  else if (min_frame_size >= 480) { K.sad_lambda = 15; K.sse_lambda = 0; }
+  if (min_cm_size >= 720) { K.sad_lambda = 8; K.sse_lambda = 1; }
+  else if (min_cm_size >= 480) { K.sad_lambda = 15; K.sse_lambda = 0; }
   else { K.sad_lambda = 32; K.sse_lambda = 2; }
   {  // av1_init_search_range (mcomp.c:217-226)
     int size = K.width > K.height ? K.width : K.height;
@@ -393,7 +430,7 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     while ((size << sr) < 1023) sr++;
     K.step_param = sr < 9 ? sr : 9;
   }
-  K.mse_thresh = ((min_frame_size >= 720) ? 12 : 3) << (p->bit_depth - 8);  // temporal_filter.c:249-250
+  K.mse_thresh = ((min_cm_size >= 720) ? 12 : 3) << (p->bit_depth - 8);  // temporal_filter.c:249-250
   K.hbd_shift = g.is_hbd ? (p->bit_depth == 10 ? 2 : (p->bit_depth == 12 ? 4 : 0)) : 0;
   {  // decay factors, temporal_filter.c:583-597 (host libm, as the reference)
     double q_decay = pow((double)p->q_factor / 20, 2);
@@ -459,7 +496,7 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   const int nref = p->num_frames - 1;
   // the frame to filter is read by every kernel
   CU(cudaStreamWaitEvent(ctx->stream, frames[p->filter_frame_idx]->ready, 0));
-  if (timed) CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (timed) CU(cudaEventRecord(te->ev0, ctx->stream));
   // Search phase: one search32 launch per reference frame on the main stream (the ref_mv
   // chain), the independent 16x16 searches of that frame on a second stream as soon as its
   // 32x32 results exist -> the throughput-bound 16x16 work fills the latency-bound chain.
@@ -496,12 +533,12 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
         any16 = true;
       }
     }
-    if (timed) cudaEventRecord(ctx->evk[0], ctx->stream);
+    if (timed) cudaEventRecord(te->evk[0], ctx->stream);
     if (any16) {
       CU(cudaEventRecord(ctx->ev_s16, ctx->stream2));
       CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_s16, 0));
     }
-    if (timed) cudaEventRecord(ctx->evk[1], ctx->stream);
+    if (timed) cudaEventRecord(te->evk[1], ctx->stream);
   }
   // the filter kernel overwrites the device output: the previous call's read-back must be over
   if (ctx->out_done_valid) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out_done, 0));
@@ -509,9 +546,10 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   else tf_filter_kernel<uint8_t><<<grid, FILT_THREADS, smem_filter, ctx->stream>>>(K);
   nlaunch++;
   CU(cudaGetLastError());
-  if (timed) CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (timed) CU(cudaEventRecord(te->ev1, ctx->stream));
   ctx->last_launches += nlaunch - 1;
   ctx->split_valid = timed && nref > 0;
+  if (timed) ctx->last_ev = te;
   ctx->last_launches++;
   return TF_GPU_OK;
 }
@@ -611,7 +649,8 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
   for (int i = 0; i < params->num_frames; i++)
     if (!(devf[i]->g == devf[0]->g)) return fail(ctx, TF_GPU_ERR_INVALID, "frames of one window must share geometry");
   const Geometry &g = devf[0]->g;
-  if (g.is_hbd == 0 && params->bit_depth != 8) return fail(ctx, TF_GPU_ERR_INVALID, "8-bit container needs bit_depth 8");
+  rc = validate_geometry(ctx, params, g);
+  if (rc) return rc;
   Geometry og = g;
   const bool extend_out = params->extend_output_borders && !(params->out_row_end > params->out_row_begin);
   if (extend_out) {
@@ -631,7 +670,7 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
   const int slot = (int)(ctx->next_ticket % 8);
   unsigned long long *d_diff = ctx->d_diff + 2 * slot;
   CU(cudaMemsetAsync(d_diff, 0, 2 * sizeof(unsigned long long), ctx->stream));
-  rc = launch_filter(ctx, params, devf, g, d_diff, dump, true);
+  rc = launch_filter(ctx, params, devf, g, d_diff, dump, &t.te);
   if (rc) return rc;
   const int mb_rows = (g.crop_h[0] + 31) / 32;
   int rb = 0, re = mb_rows;
@@ -719,12 +758,20 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_s16, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
-  if (e == cudaSuccess) e = cudaEventCreate(&ctx->evk[0]);
-  if (e == cudaSuccess) e = cudaEventCreate(&ctx->evk[1]);
+  auto make_call_events = [&](CallEvents &te) {
+    if (e == cudaSuccess) e = cudaEventCreate(&te.ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&te.ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&te.evk[0]);
+    if (e == cudaSuccess) e = cudaEventCreate(&te.evk[1]);
+  };
+  make_call_events(ctx->res_ev);
+  for (int i = 0; i < 8; i++) make_call_events(ctx->tickets[i].te);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->noise_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_async_upload, cudaEventDisableTiming);
   for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->user_ev[i]);
   for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&ctx->tickets[i].ev, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_diff, 16 * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_diff, 16 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_diff, 18 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_diff, 18 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_noise, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctr, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_noise, 2 * sizeof(unsigned long long));
@@ -775,8 +822,19 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
     if (ctx->tickets[i].ev) cudaEventDestroy(ctx->tickets[i].ev);
   for (int i = 0; i < 4; i++)
     if (ctx->user_ev[i]) cudaEventDestroy(ctx->user_ev[i]);
-  if (ctx->evk[0]) cudaEventDestroy(ctx->evk[0]);
-  if (ctx->evk[1]) cudaEventDestroy(ctx->evk[1]);
+  auto drop_call_events = [](CallEvents &te) {
+    if (te.ev0) cudaEventDestroy(te.ev0);
+    if (te.ev1) cudaEventDestroy(te.ev1);
+    if (te.evk[0]) cudaEventDestroy(te.evk[0]);
+    if (te.evk[1]) cudaEventDestroy(te.evk[1]);
+  };
+  drop_call_events(ctx->res_ev);
+  for (int i = 0; i < 8; i++) drop_call_events(ctx->tickets[i].te);
+  if (ctx->noise_stream) {
+    cudaStreamSynchronize(ctx->noise_stream);
+    cudaStreamDestroy(ctx->noise_stream);
+  }
+  if (ctx->ev_async_upload) cudaEventDestroy(ctx->ev_async_upload);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int i = 0; i < TF_GPU_MAX_FRAMES; i++)
@@ -805,6 +863,44 @@ int tf_gpu_cache_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *frame) {
   return TF_GPU_OK;
 }
 
+int tf_gpu_cache_frame_async(tf_gpu_ctx *ctx, const tf_gpu_frame *frame) {
+  if (!ctx || !frame) return TF_GPU_ERR_INVALID;
+  if (!frame->frame_id) return fail(ctx, TF_GPU_ERR_INVALID, "frame_id 0 cannot be cached");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->async_upload_pending) {  // at most one asynchronous upload outstanding (see tf_gpu.h)
+    CU(cudaEventSynchronize(ctx->ev_async_upload));
+    ctx->async_upload_pending = false;
+  }
+  CallScope scope(ctx);
+  DevFrame *d;
+  const int num_planes = frame->plane[1] ? 3 : 1;
+  int rc = get_frame(ctx, frame, num_planes, &d);
+  if (rc) return rc;
+  CU(cudaEventRecord(ctx->ev_async_upload, ctx->copy_stream));
+  ctx->async_upload_pending = true;
+  return TF_GPU_OK;
+}
+
+int tf_gpu_device_border(void) { return DEV_BORDER; }
+
+int tf_gpu_debug_read_plane(tf_gpu_ctx *ctx, uint64_t frame_id, int plane, void *dst, int dst_stride, int x0, int y0,
+                            int w, int h) {
+  if (!ctx || !dst || plane < 0 || plane > 2 || w <= 0 || h <= 0) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  DevFrame *d = find_cached(ctx, frame_id, nullptr);
+  if (!d) return fail(ctx, TF_GPU_ERR_INVALID, "frame id %llu is not resident", (unsigned long long)frame_id);
+  const Geometry &g = d->g;
+  if (plane >= g.num_planes) return fail(ctx, TF_GPU_ERR_INVALID, "plane not present");
+  const int k = plane > 0;
+  const size_t es = g.is_hbd ? 2 : 1;
+  if (x0 < -g.bx[k] || y0 < -g.by[k] || x0 + w > g.pitch[k] - g.bx[k] || y0 + h > g.rows[k] - g.by[k])
+    return fail(ctx, TF_GPU_ERR_INVALID, "rectangle outside the device allocation");
+  CU(cudaStreamSynchronize(ctx->copy_stream));
+  const char *src = (const char *)d->p00[plane] + ((long long)y0 * g.pitch[k] + x0) * (long long)es;
+  CU(cudaMemcpy2D(dst, (size_t)dst_stride * es, src, (size_t)g.pitch[k] * es, (size_t)w * es, h, cudaMemcpyDeviceToHost));
+  return TF_GPU_OK;
+}
+
 int tf_gpu_evict_frame(tf_gpu_ctx *ctx, uint64_t frame_id) {
   if (!ctx) return TF_GPU_ERR_INVALID;
   for (auto &d : ctx->cache)
@@ -816,33 +912,36 @@ int tf_gpu_estimate_noise(tf_gpu_ctx *ctx, const tf_gpu_frame *frame, int plane,
                           double *noise_level) {
   if (!ctx || !frame || !noise_level) return TF_GPU_ERR_INVALID;
   if (plane < 0 || plane > 2) return fail(ctx, TF_GPU_ERR_INVALID, "plane out of range");
+  if (bit_depth != 8 && bit_depth != 10 && bit_depth != 12) return fail(ctx, TF_GPU_ERR_INVALID, "bit_depth must be 8, 10 or 12");
+  if (!frame->is_hbd && bit_depth != 8) return fail(ctx, TF_GPU_ERR_INVALID, "8-bit container needs bit_depth 8");
   CU(cudaSetDevice(ctx->device));
   CallScope scope(ctx);
   ctx->last_launches = 0;
+  cudaStream_t ns = ctx->noise_stream;  // not the main stream: a window submitted earlier keeps running
   DevFrame *d;
   const int num_planes = frame->plane[1] ? 3 : 1;
   if (plane >= num_planes) return fail(ctx, TF_GPU_ERR_INVALID, "plane not present");
   int rc = get_frame(ctx, frame, num_planes, &d);
   if (rc) return rc;
-  CU(cudaStreamWaitEvent(ctx->stream, d->ready, 0));
+  CU(cudaStreamWaitEvent(ns, d->ready, 0));
   const Geometry &g = d->g;
   const int k = plane > 0;
   const int w = g.crop_w[k], h = g.crop_h[k];
-  CU(cudaMemsetAsync(ctx->d_noise, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_noise, 0, 2 * sizeof(unsigned long long), ns));
   if (w > 2 && h > 2) {
     const long long n = (long long)(w - 2) * (h - 2);
     const int threads = 256;
     long long blocks = (n + threads - 1) / threads;
     if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
     if (g.is_hbd)
-      noise_kernel<uint16_t><<<(int)blocks, threads, 0, ctx->stream>>>((const uint16_t *)d->p00[plane], g.pitch[k], w, h, bit_depth, edge_thresh, ctx->d_noise);
+      noise_kernel<uint16_t><<<(int)blocks, threads, 0, ns>>>((const uint16_t *)d->p00[plane], g.pitch[k], w, h, bit_depth, edge_thresh, ctx->d_noise);
     else
-      noise_kernel<uint8_t><<<(int)blocks, threads, 0, ctx->stream>>>((const uint8_t *)d->p00[plane], g.pitch[k], w, h, bit_depth, edge_thresh, ctx->d_noise);
+      noise_kernel<uint8_t><<<(int)blocks, threads, 0, ns>>>((const uint8_t *)d->p00[plane], g.pitch[k], w, h, bit_depth, edge_thresh, ctx->d_noise);
     CU(cudaGetLastError());
     ctx->last_launches++;
   }
-  CU(cudaMemcpyAsync(ctx->h_noise, ctx->d_noise, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_noise, ctx->d_noise, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ns));
+  CU(cudaStreamSynchronize(ns));
   const long long accum = (long long)ctx->h_noise[0];
   const int count = (int)ctx->h_noise[1];
   // temporal_filter.c:1193, SQRT_PI_BY_2 :1148
@@ -868,7 +967,8 @@ int tf_gpu_wait(tf_gpu_ctx *ctx, uint64_t ticket) {
     t.diff_dst[1] = (int64_t)ctx->h_diff[2 * (ticket % 8) + 1];
   }
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_kernel_ms = ms;
+  if (cudaEventElapsedTime(&ms, t.te.ev0, t.te.ev1) == cudaSuccess) ctx->last_kernel_ms = ms;
+  ctx->last_ev = &t.te;
   return TF_GPU_OK;
 }
 
@@ -901,13 +1001,16 @@ int tf_gpu_filter_resident_async(tf_gpu_ctx *ctx, const tf_gpu_params *params, c
     devf[i]->pinned_epoch = ctx->epoch;
   }
   const Geometry &g = devf[0]->g;
-  if (g.num_planes < params->num_planes) return fail(ctx, TF_GPU_ERR_INVALID, "resident frames lack chroma planes");
+  rc = validate_geometry(ctx, params, g);
+  if (rc) return rc;
   rc = alloc_dev_frame(ctx, &ctx->out, g);
   if (rc) return rc;
-  CU(cudaMemsetAsync(ctx->d_diff, 0, 2 * sizeof(unsigned long long), ctx->stream));
-  rc = launch_filter(ctx, params, devf, g, ctx->d_diff, nullptr, true);
+  // slot 8 of the FRAME_DIFF ring belongs to the resident path (slots 0..7: tickets)
+  unsigned long long *d_diff = ctx->d_diff + 2 * 8;
+  CU(cudaMemsetAsync(d_diff, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  rc = launch_filter(ctx, params, devf, g, d_diff, nullptr, &ctx->res_ev);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->h_diff, ctx->d_diff, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->h_diff + 2 * 8, d_diff, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   return TF_GPU_OK;
 }
 
@@ -916,11 +1019,12 @@ int tf_gpu_filter_resident_result(tf_gpu_ctx *ctx, int64_t diff_sum_sse[2], floa
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
   if (diff_sum_sse) {
-    diff_sum_sse[0] = (int64_t)ctx->h_diff[0];
-    diff_sum_sse[1] = (int64_t)ctx->h_diff[1];
+    diff_sum_sse[0] = (int64_t)ctx->h_diff[2 * 8];
+    diff_sum_sse[1] = (int64_t)ctx->h_diff[2 * 8 + 1];
   }
   float ms = 0.f;
-  CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  CU(cudaEventElapsedTime(&ms, ctx->res_ev.ev0, ctx->res_ev.ev1));
+  ctx->last_ev = &ctx->res_ev;
   ctx->last_kernel_ms = ms;
   if (time_ms) *time_ms = ms;
   return TF_GPU_OK;
@@ -995,12 +1099,13 @@ int tf_gpu_read_counters(tf_gpu_ctx *ctx, uint64_t counters[4]) {
 int tf_gpu_last_kernel_times(tf_gpu_ctx *ctx, float ms[3]) {
   if (!ctx || !ms) return TF_GPU_ERR_INVALID;
   ms[0] = ms[1] = ms[2] = 0.f;
-  if (!ctx->split_valid) return TF_GPU_OK;
+  if (!ctx->split_valid || !ctx->last_ev) return TF_GPU_OK;
+  const CallEvents &te = *ctx->last_ev;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaEventSynchronize(ctx->ev1));
-  CU(cudaEventElapsedTime(&ms[0], ctx->ev0, ctx->evk[0]));
-  CU(cudaEventElapsedTime(&ms[1], ctx->evk[0], ctx->evk[1]));
-  CU(cudaEventElapsedTime(&ms[2], ctx->evk[1], ctx->ev1));
+  CU(cudaEventSynchronize(te.ev1));
+  CU(cudaEventElapsedTime(&ms[0], te.ev0, te.evk[0]));
+  CU(cudaEventElapsedTime(&ms[1], te.evk[0], te.evk[1]));
+  CU(cudaEventElapsedTime(&ms[2], te.evk[1], te.ev1));
   return TF_GPU_OK;
 }
 
@@ -1032,6 +1137,8 @@ int tf_gpu_synchronize(tf_gpu_ctx *ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaStreamSynchronize(ctx->out_stream));
   CU(cudaStreamSynchronize(ctx->copy_stream));
+  CU(cudaStreamSynchronize(ctx->noise_stream));
+  ctx->async_upload_pending = false;
   return TF_GPU_OK;
 }
 

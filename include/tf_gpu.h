@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TF_GPU_ABI_VERSION 1
+#define TF_GPU_ABI_VERSION 2
 #define TF_GPU_MAX_FRAMES 24 /* reference: arnr_max_frames 15 + adjust 6 = 21 (temporal_filter.c:997,1063-1080) */
 
 enum {
@@ -94,7 +94,12 @@ typedef struct {
    * av1_temporal_filter at temporal_filter.c:1372, encode_strategy.c:822) on the device and return the
    * whole extended allocation of `out` (needs out->border and out->stride to describe it). */
   int extend_output_borders;
-  int reserved[7];
+  /* cm->width / cm->height: tf_motion_search() picks the MV cost class and the ref_mv reset
+   * threshold from AOMMIN(cm->width, cm->height) (temporal_filter.c:99-100,119-122,249-250), which is
+   * the CODED size and differs from the source crop size under superres / spatial resize.
+   * 0 = use the luma crop size of the frames. */
+  int cm_width, cm_height;
+  int reserved[5];
 } tf_gpu_params;
 
 /* Per-(block, frame) intermediate state for parity tests (what a debug build of
@@ -152,7 +157,20 @@ int tf_gpu_wait(tf_gpu_ctx *ctx, uint64_t ticket);
  * lookahead.c:101-163) so that tf_gpu_filter never waits on PCIe; drop it when
  * it leaves. */
 int tf_gpu_cache_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *frame);
+/* Same without waiting for the copy: the call first waits for the PREVIOUS asynchronous upload of
+ * this context, then enqueues this one and returns.  So at most one upload is outstanding and a
+ * host buffer may be rewritten as soon as one later tf_gpu_cache_frame_async() (or any
+ * tf_gpu_synchronize / tf_gpu_wait that covers it) has returned -- which is what a lookahead ring
+ * needs: a slot is only rewritten by a later av1_lookahead_push (lookahead.c:126,150). */
+int tf_gpu_cache_frame_async(tf_gpu_ctx *ctx, const tf_gpu_frame *frame);
 int tf_gpu_evict_frame(tf_gpu_ctx *ctx, uint64_t frame_id);
+/* Test hook for the upload path (av1_copy_and_extend_frame, extend.c:113-163): copies the rectangle
+ * [x0, x0+w) x [y0, y0+h) of a cached device plane (coordinates relative to pixel (0,0); negative =
+ * border) into dst (samples of the frame's container type, dst_stride in samples).  The rectangle
+ * must lie inside the device allocation (tf_gpu_device_border() samples of luma border). */
+int tf_gpu_debug_read_plane(tf_gpu_ctx *ctx, uint64_t frame_id, int plane, void *dst, int dst_stride,
+                            int x0, int y0, int w, int h);
+int tf_gpu_device_border(void);
 
 /* Device-resident variant used by the benchmark's kernel-only number and by the
  * multi-GPU slab mode: frames must already be cached (ids), output stays on the

@@ -211,6 +211,8 @@ typedef struct {
   tfref_frame *frames;
   tfref_frame out;
   int num_planes, num_pels, mb_rows, mb_cols;
+  const YV12_BUFFER_CONFIG *la_frames[32]; /* seam tests: the window inside a real lookahead */
+  int use_lookahead;
 } tfref_ctx;
 
 static void set_fn_ptrs(AV1_PRIMARY *ppi, int use_hbd, int bd) {
@@ -369,7 +371,8 @@ static void tfref_setup_tf_ctx(tfref_ctx *t) {
   AV1_COMP *cpi = t->cpi;
   const tfref_cfg *c = &t->cfg;
   TemporalFilterCtx *tf_ctx = &cpi->tf_ctx;
-  for (int i = 0; i < c->num_frames; i++) tf_ctx->frames[i] = &t->frames[i].buf;
+  for (int i = 0; i < c->num_frames; i++)
+    tf_ctx->frames[i] = (YV12_BUFFER_CONFIG *)(t->use_lookahead ? t->la_frames[i] : &t->frames[i].buf);
   tf_ctx->num_frames = c->num_frames;
   tf_ctx->filter_frame_idx = c->filter_frame_idx;
   tf_ctx->output_frame = &t->out.buf;
@@ -385,15 +388,24 @@ static void tfref_setup_tf_ctx(tfref_ctx *t) {
 }
 
 #if CONFIG_TF_GPU
-/* Runs the reference-side CONFIG_TF_GPU seam (integration/tf_gpu_seam.patch): the exact
- * code a maintainer adds to av1_temporal_filter(), filling tf_gpu_params / tf_gpu_frame
- * from AV1_COMP and calling libtf_gpu.so. */
+/* The reference-side CONFIG_TF_GPU seam (integration/tf_gpu_seam.patch), driven hunk by hunk: the
+ * exact code a maintainer adds, filling tf_gpu_params / tf_gpu_frame from AV1_COMP and calling
+ * libtf_gpu.so. */
 /* The patch's replacement for the noise-estimation loop of tf_setup_filtering_buffer(). */
 TFREF_API void tfref_gpu_noise_levels(void *h, int idx, double *noise_levels) {
   tfref_ctx *t = (tfref_ctx *)h;
   tf_gpu_noise_levels(t->cpi, &t->frames[idx].entry, noise_levels);
 }
 
+/* av1_tf_gpu_estimate_noise() as the key-frame gate (encode_strategy.c:746-750, in_lookahead = 1) and the
+ * ALLINTRA noise synthesis (encoder.c:4038-4051, in_lookahead = 0, edge threshold 16) call it. */
+TFREF_API double tfref_gpu_estimate_noise(void *h, int idx, int in_lookahead, int plane, int edge_thresh) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  return av1_tf_gpu_estimate_noise(t->cpi, &t->frames[idx].buf, in_lookahead, plane, t->cfg.bit_depth,
+                                   edge_thresh);
+}
+
+/* av1_temporal_filter()'s branch: the synchronous call. */
 TFREF_API void tfref_run_gpu_seam(void *h, int64_t *diff_sum_sse) {
   tfref_ctx *t = (tfref_ctx *)h;
   tfref_setup_tf_ctx(t);
@@ -403,6 +415,72 @@ TFREF_API void tfref_run_gpu_seam(void *h, int64_t *diff_sum_sse) {
     diff_sum_sse[0] = fd.sum;
     diff_sum_sse[1] = fd.sse;
   }
+}
+
+/* av1_tf_info_filtering()'s branch: `copies` submits of the same window back to back (as the KF and ARF
+ * windows of a GOP), waited for together; the output comes back with aom_extend_frame_borders() already
+ * applied on the device.  Every copy writes t->out; diff_sum_sse receives the last one's FRAME_DIFF and
+ * *all_equal whether every copy reported the same. */
+TFREF_API void tfref_run_gpu_seam_async(void *h, int copies, int64_t *diff_sum_sse, int *all_equal) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  tfref_setup_tf_ctx(t);
+  uint64_t ticket[8];
+  int64_t diff[8][2];
+  if (copies > 8) copies = 8;
+  for (int i = 0; i < copies; i++) ticket[i] = tf_gpu_submit_filtering(t->cpi, diff[i]);
+  FRAME_DIFF fd = { 0, 0 };
+  *all_equal = 1;
+  for (int i = 0; i < copies; i++) {
+    tf_gpu_wait_filtering(t->cpi, ticket[i], diff[i], &fd);
+    if (diff[i][0] != diff[0][0] || diff[i][1] != diff[0][1]) *all_equal = 0;
+  }
+  diff_sum_sse[0] = fd.sum;
+  diff_sum_sse[1] = fd.sse;
+}
+
+/* The av1_receive_raw_frame() hunk: a real lookahead (av1_lookahead_init / av1_lookahead_push), every
+ * pushed frame uploaded by av1_tf_gpu_lookahead_push(); afterwards the window's frames[] point at the
+ * lookahead entries, as tf_setup_filtering_buffer() leaves them. */
+TFREF_API int tfref_gpu_push_window(void *h) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  const tfref_cfg *c = &t->cfg;
+  AV1_COMP *cpi = t->cpi;
+  if (!t->ppi->lookahead)
+    t->ppi->lookahead = av1_lookahead_init(c->width, c->height, c->ss_x, c->ss_y, c->use_hbd,
+                                           c->num_frames, c->border, 0, 0, false, 0);
+  if (!t->ppi->lookahead) return -1;
+  cpi->compressor_stage = ENCODE_STAGE;
+  cpi->oxcf.pass = AOM_RC_ONE_PASS;
+  t->ppi->tf_info.is_temporal_filter_on = 1;
+  for (int i = 0; i < c->num_frames; i++) {
+    if (av1_lookahead_push(t->ppi->lookahead, &t->frames[i].buf, i, i + 1, c->use_hbd, 0, 0)) return -2;
+    av1_tf_gpu_lookahead_push(cpi);
+  }
+  for (int i = 0; i < c->num_frames; i++) {
+    struct lookahead_entry *e = av1_lookahead_peek(t->ppi->lookahead, i, ENCODE_STAGE);
+    if (!e) return -3;
+    t->la_frames[i] = &e->img;
+  }
+  t->use_lookahead = 1;
+  return 0;
+}
+
+/* kernel launches of the last library call on the seam's context (uploads show up as border kernels) */
+TFREF_API int tfref_gpu_last_launches(void *h) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  int n = -1;
+  if (t->ppi->tf_info.gpu) tf_gpu_last_stats(t->ppi->tf_info.gpu, &n, NULL);
+  return n;
+}
+TFREF_API int tfref_gpu_num_pinned(void *h) { return ((tfref_ctx *)h)->ppi->tf_info.gpu_num_pinned; }
+TFREF_API int tfref_gpu_has_context(void *h) { return ((tfref_ctx *)h)->ppi->tf_info.gpu != NULL; }
+/* av1_tf_info_free()'s hunk: the context dies with the TEMPORAL_FILTER_INFO */
+TFREF_API void tfref_gpu_release(void *h) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  const int on = t->ppi->tf_info.is_temporal_filter_on;
+  t->ppi->tf_info.is_temporal_filter_on = 0; /* the harness owns no tf_buf[] */
+  av1_tf_info_free(&t->ppi->tf_info);
+  t->ppi->tf_info.is_temporal_filter_on = on;
 }
 #endif
 
@@ -480,6 +558,10 @@ TFREF_API void tfref_extend_output_borders(void *h) {
 TFREF_API void tfref_destroy(void *h) {
   tfref_ctx *t = (tfref_ctx *)h;
   if (!t) return;
+#if CONFIG_TF_GPU
+  tfref_gpu_release(h);
+  if (t->ppi->lookahead) av1_lookahead_destroy(t->ppi->lookahead);
+#endif
   for (int i = 0; i < t->cfg.num_frames; i++) aom_free_frame_buffer(&t->frames[i].buf);
   aom_free_frame_buffer(&t->out.buf);
   free(t->frames);

@@ -14,3 +14,6 @@ STUB_ABORT(aom_alloc_pyramid)
 size_t aom_get_pyramid_alloc_size(void) { return 0; }
 void aom_free_pyramid(void *p) { (void)p; }
 void aom_img_metadata_array_free(void *p) { (void)p; }
+/* av1_lookahead_push() copies frame metadata; the harness frames carry none (seam build only) */
+STUB_ABORT(aom_img_metadata_array_alloc)
+STUB_ABORT(aom_img_metadata_alloc)

@@ -67,6 +67,14 @@ def seam_lib():
         _seam = _bind(C.CDLL(SEAM_LIB))
         _seam.tfref_run_gpu_seam.argtypes = [C.c_void_p, C.c_void_p]
         _seam.tfref_gpu_noise_levels.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        _seam.tfref_gpu_estimate_noise.restype = C.c_double
+        _seam.tfref_gpu_estimate_noise.argtypes = [C.c_void_p] + [C.c_int] * 4
+        _seam.tfref_run_gpu_seam_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        _seam.tfref_gpu_push_window.argtypes = [C.c_void_p]
+        _seam.tfref_gpu_last_launches.argtypes = [C.c_void_p]
+        _seam.tfref_gpu_num_pinned.argtypes = [C.c_void_p]
+        _seam.tfref_gpu_has_context.argtypes = [C.c_void_p]
+        _seam.tfref_gpu_release.argtypes = [C.c_void_p]
     return _seam
 
 
@@ -77,6 +85,12 @@ def _bind(l):
     l.tfref_run.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
     l.tfref_get_output.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
     l.tfref_destroy.argtypes = [C.c_void_p]
+    l.tfref_estimate_noise.restype = C.c_double
+    l.tfref_estimate_noise.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    l.tfref_frame_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 5
+    l.tfref_get_plane_with_border.restype = C.c_int
+    l.tfref_get_plane_with_border.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    l.tfref_extend_output_borders.argtypes = [C.c_void_p]
     return l
 
 
@@ -142,7 +156,7 @@ class RefFilter:
 
     def estimate_noise(self, idx=None):
         idx = self.p["filter_frame_idx"] if idx is None else idx
-        return [lib().tfref_estimate_noise(self.h, idx, pl) for pl in range(self.num_planes)]
+        return [self.L.tfref_estimate_noise(self.h, idx, pl) for pl in range(self.num_planes)]
 
     def run(self, record=True, rows=None):
         nb = self.mb_rows * self.mb_cols
@@ -178,15 +192,34 @@ class RefFilter:
         self.L.tfref_run_gpu_seam(self.h, _ptr(diff))
         return dict(out=self._outputs(), diff=diff)
 
+    def run_gpu_seam_async(self, copies=2):
+        """av1_tf_info_filtering()'s CONFIG_TF_GPU branch: `copies` windows submitted back to back and waited
+        for together; the output frame comes back with its borders extended on the device."""
+        diff = np.zeros(2, np.int64)
+        eq = C.c_int(0)
+        self.L.tfref_run_gpu_seam_async(self.h, copies, _ptr(diff), C.byref(eq))
+        return dict(out=self._outputs(), diff=diff, all_equal=bool(eq.value))
+
+    def gpu_push_window(self):
+        """Real lookahead + the av1_receive_raw_frame() hunk: every pushed frame is uploaded at push time."""
+        rc = self.L.tfref_gpu_push_window(self.h)
+        assert rc == 0, rc
+
+    def gpu_estimate_noise(self, idx, in_lookahead, plane, edge_thresh=50):
+        return self.L.tfref_gpu_estimate_noise(self.h, idx, int(in_lookahead), plane, edge_thresh)
+
+    def extend_output_borders(self):
+        self.L.tfref_extend_output_borders(self.h)
+
     def plane_with_border(self, idx, plane):
         ys, uvs, b, aw, ah = (C.c_int() for _ in range(5))
-        lib().tfref_frame_info(self.h, ys, uvs, b, aw, ah)
+        self.L.tfref_frame_info(self.h, ys, uvs, b, aw, ah)
         stride = uvs.value if plane else ys.value
         bh = b.value >> (self.p["ss_y"] if plane else 0)
         ph = (ah.value >> (self.p["ss_y"] if plane else 0)) + 2 * bh
         buf = np.zeros((ph, stride), np.uint16)
         rows = C.c_int()
-        s = lib().tfref_get_plane_with_border(self.h, idx, plane, _ptr(buf), C.byref(rows))
+        s = self.L.tfref_get_plane_with_border(self.h, idx, plane, _ptr(buf), C.byref(rows))
         assert s == stride and rows.value == ph
         return buf, dict(y_stride=ys.value, uv_stride=uvs.value, border=b.value,
                          aligned_w=aw.value, aligned_h=ah.value)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = pkg.load_library()
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.tf_gpu_abi_version() == 1
+    assert lib.tf_gpu_abi_version() == 2
 
 
 def test_struct_layouts(pkg):

@@ -188,3 +188,36 @@ def test_output_border_extension_matches_reference(pkg, tfgpu, case):
         assert ref_plane.shape == out.alloc[pl].shape
         assert (ref_plane == out.alloc[pl]).all(), pl
     r.close()
+
+
+@pytest.mark.parametrize("dims", [(352, 288, 8, 1, 1, 96), (131, 77, 10, 1, 1, 160), (130, 70, 8, 0, 0, 160), (1920, 1080, 10, 1, 1, 160)],
+                         ids=["cif8", "odd10", "odd_i444", "1080p10"])
+def test_device_input_plane_border_equals_copy_and_extend_frame(pkg, tfgpu, dims):
+    """SURVEY 8a row 2, read back directly: only the crop area of a host frame crosses PCIe and
+    extend_borders_kernel rebuilds the replication; the device plane -- border included, as far as the device
+    border reaches -- must be sample-identical to what the reference's av1_copy_and_extend_frame
+    (av1/encoder/extend.c:113-163) leaves in the lookahead slot."""
+    import _ref
+    if not _ref.available():
+        pytest.skip("oracle/_ref/libtf_ref.so not built")
+    W, H, bd, sx, sy, border = dims
+    frames = _clips.moving_texture(W, H, 1, bd, ss_x=sx, ss_y=sy)
+    p = _params.tf_params(W, H, 1, bit_depth=bd, ss_x=sx, ss_y=sy, border=border)
+    r = _ref.RefFilter(p, frames)
+    # host frame WITHOUT borders: whatever lies outside the crop area on the device was built there
+    b = pkg.Yv12Buffer(W, H, sx, sy, bd > 8, border, frame_id=777000 + W).set_planes(*frames[0], extend=False)
+    tfgpu.cache_frame(b)
+    db = tfgpu.device_border()
+    for pl in range(3):
+        k = 1 if pl else 0
+        ref_plane, info = r.plane_with_border(0, pl)
+        hb_x, hb_y = b.borders[k]
+        aw, ah = b.aligned[k]
+        ex = min(db >> (sx if pl else 0), hb_x)
+        ey = min(db >> (sy if pl else 0), hb_y)
+        got = tfgpu.debug_read_plane(b, pl, -ex, -ey, aw + 2 * ex, ah + 2 * ey)
+        want = ref_plane[hb_y - ey:hb_y + ah + ey, hb_x - ex:hb_x + aw + ex]
+        assert got.shape == want.shape
+        assert (got.astype(np.uint16) == want).all(), (pl, int((got.astype(np.uint16) != want).sum()))
+    tfgpu.evict_frame(b.frame_id)
+    r.close()

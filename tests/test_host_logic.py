@@ -78,7 +78,9 @@ def test_seam_patch_applies_to_the_reference(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     patch = os.path.join(root, "integration", "tf_gpu_seam.patch")
     files = re.findall(r"^--- a/(\S+)$", open(patch).read(), re.M)
-    assert sorted(files) == ["CMakeLists.txt", "av1/encoder/temporal_filter.c", "build/cmake/aom_config_defaults.cmake"]
+    assert sorted(files) == ["CMakeLists.txt", "av1/encoder/encode_strategy.c", "av1/encoder/encoder.c",
+                             "av1/encoder/temporal_filter.c", "av1/encoder/temporal_filter.h",
+                             "build/cmake/aom_config_defaults.cmake"]
     for rel in files:
         os.makedirs(os.path.dirname(tmp_path / rel), exist_ok=True)
         shutil.copyfile(os.path.join("/root/reference", rel), tmp_path / rel)
@@ -86,3 +88,11 @@ def test_seam_patch_applies_to_the_reference(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     patched = open(tmp_path / "av1/encoder/temporal_filter.c").read()
     assert "tf_gpu_do_filtering(cpi, frame_diff);" in patched and "tf_gpu_noise_levels(cpi, to_filter_buf, noise_levels);" in patched
+    # every caller the seam covers: submit/wait in av1_tf_info_filtering, context freed with the
+    # TEMPORAL_FILTER_INFO, upload at lookahead push, the two other noise-estimate callers
+    assert "tf_gpu_submit_filtering(cpi, gpu_diff[buf_idx]);" in patched and "tf_gpu_release(tf_info);" in patched
+    assert "av1_tf_gpu_lookahead_push(cpi);" in open(tmp_path / "av1/encoder/encoder.c").read()
+    assert "av1_tf_gpu_estimate_noise(cpi, sd, 0, 0," in open(tmp_path / "av1/encoder/encoder.c").read()
+    assert "av1_tf_gpu_estimate_noise(" in open(tmp_path / "av1/encoder/encode_strategy.c").read()
+    assert "struct tf_gpu_ctx *gpu;" in open(tmp_path / "av1/encoder/temporal_filter.h").read()
+    assert "static tf_gpu_ctx *tf_gpu_instance" not in patched  # no process-wide context

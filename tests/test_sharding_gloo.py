@@ -1,7 +1,8 @@
-"""CPU, world_size 2, gloo: the slab-parallel multi-GPU path with the oracle
-standing in for the kernels -- each rank filters its block-row range of the same window,
-rows are gathered on rank 0 and FRAME_DIFF is all-reduced; the result equals the
-single-process run bit for bit (integer sums are order independent)."""
+"""CPU, world_size 2, gloo: the slab-parallel multi-GPU driver (aom_av1_psy_b200.sharding.SlabWindow, the
+code bench.py's slab mode and the NCCL test run on GPUs) with the oracle standing in for the kernels -- each
+rank filters its block-row range of the same window, SlabWindow.gather() collects the slabs on rank 0 and
+all-reduces FRAME_DIFF, SlabWindow.assemble() rebuilds the planes; the result equals the single-process run
+bit for bit (integer sums are order independent)."""
 import os
 import sys
 
@@ -30,27 +31,27 @@ def _worker(rank, world, port, q):
     frames = _clips.moving_texture(W, H, N, 8)
     p = _params.tf_params(W, H, N)
     mb_rows = (H + 31) // 32
-    b, e = sh.slab_rows(mb_rows, world, rank)
+    slab = sh.SlabWindow(mb_rows, world, rank)
+    ps = slab.params(p)
+    assert (ps["out_row_begin"], ps["out_row_end"]) == sh.slab_rows(mb_rows, world, rank)
     o = _oracle.OracleFilter(p, frames)
-    r = o.run(rows=(b, e))
-    pad = sh.max_slab_rows(mb_rows, world)
-    gathered = []
-    for pl in range(3):
-        bh = 32 >> (1 if pl else 0)
-        slab = np.zeros((pad * bh, r["out"][pl].shape[1]), np.int32)
-        slab[: (e - b) * bh] = r["out"][pl][b * bh:e * bh]
-        t = torch.from_numpy(slab)
-        lst = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, lst, dst=0)
-        if rank == 0:
-            gathered.append(sh.merge_slabs([x.numpy() for x in lst], mb_rows, world, bh))
-    d = torch.from_numpy(r["diff"].copy())
-    dist.all_reduce(d)
+    r = o.run(rows=(slab.begin, slab.end))
+    mine, pitch = [], []
+    for pl, bh in enumerate(slab.block_h):
+        width = r["out"][pl].shape[1]
+        buf = np.zeros((slab.pad_rows * bh, width), np.int32)
+        buf[: (slab.end - slab.begin) * bh] = r["out"][pl][slab.begin * bh:slab.end * bh]
+        mine.append(torch.from_numpy(buf).reshape(-1))
+        pitch.append(width)
+    gathered, d = slab.gather(mine, torch.from_numpy(r["diff"].copy()), dist, torch)
     if rank == 0:
+        planes = slab.assemble(gathered, pitch, torch.cat)
         full = _oracle.OracleFilter(p, frames).run()
-        ok = all((g == f.astype(np.int32)).all() for g, f in zip(gathered, full["out"]))
+        ok = all((g.numpy() == f.astype(np.int32)).all() for g, f in zip(planes, full["out"]))
         ok = ok and (d.numpy() == full["diff"]).all()
         q.put(bool(ok))
+    else:
+        assert gathered is None
     dist.destroy_process_group()
 
 
