@@ -99,6 +99,10 @@ struct tf_gpu_ctx {
   unsigned long long *d_ctr = nullptr;    // [4] executed-work counters (instrumentation)
   unsigned long long h_ctr[4] = { 0, 0, 0, 0 };
   bool collect_counters = false;
+  // development switches (environment, read once at create): TF_GPU_S16=single launches the 16x16 searches of
+  // all frames as one grid after the chain instead of one grid per frame; TF_GPU_PRIO=flat gives every stream
+  // the same priority
+  bool s16_single_launch = false;
   unsigned long long *h_noise = nullptr;
   Ticket tickets[8];
   uint64_t next_ticket = 1;
@@ -519,7 +523,7 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
         else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, smem_search, ctx->stream>>>(Kf);
       }
       nlaunch++;
-      if (!p->force_integer_mv) {
+      if (!p->force_integer_mv && !ctx->s16_single_launch) {
         CU(cudaEventRecord(ctx->ev_f32[f], ctx->stream));
         CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_f32[f], 0));
         Kf.frame_begin = f;
@@ -534,6 +538,14 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
       }
     }
     if (timed) cudaEventRecord(te->evk[0], ctx->stream);
+    if (!p->force_integer_mv && ctx->s16_single_launch) {
+      KParams K16 = K;
+      K16.frame_begin = 0;
+      K16.frame_end = p->num_frames;
+      if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4 * nref, 32, WIN16_BYTES, ctx->stream>>>(K16);
+      else tf_search16_kernel<uint8_t><<<grid * 4 * nref, 32, WIN16_BYTES, ctx->stream>>>(K16);
+      nlaunch++;
+    }
     if (any16) {
       CU(cudaEventRecord(ctx->ev_s16, ctx->stream2));
       CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_s16, 0));
@@ -744,6 +756,12 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   // independent 16x16 searches that fill the machine underneath it
   int prio_lo = 0, prio_hi = 0;
   if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  {
+    const char *m = getenv("TF_GPU_S16");
+    ctx->s16_single_launch = m && strcmp(m, "single") == 0;
+    const char *pr = getenv("TF_GPU_PRIO");
+    if (pr && strcmp(pr, "flat") == 0) prio_hi = prio_lo;
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);

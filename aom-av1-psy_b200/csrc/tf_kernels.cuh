@@ -580,6 +580,10 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
       const bool sok = (lane < nsites) & (all_in | in_range(S.lim, sr, sc)) & (scost < bestsad);
       const int soff = (sr * S.stride + sc) * (int)sizeof(T);
       const unsigned okmask = __ballot_sync(FULL, sok);
+      // (Measured and rejected: reading a quarter of a far candidate's rows first and dropping it when that
+      // part alone reaches the incumbent -- exact, but the 32x32 search walks its far stages against the poor
+      // incumbent of a predicted start, few candidates die early, and the second dependent load round trip
+      // lengthens the chain: 45.9 vs 51.0 frames/s.)
       ncand += __popc(okmask);
 #pragma unroll 1
       for (int i0 = 0; i0 < nsites; i0 += 4) {
@@ -1433,8 +1437,121 @@ __device__ __noinline__ void convolve12(const KParams &P, const T *src, int ss, 
   }
 }
 
+// The same three variants for 16-bit containers with two samples per register.  The 12 taps of
+// MULTITAP_SHARP2 at a fractional position fit a signed byte (-26 .. 127; 128 only occurs at position 0,
+// which is the copy path), the samples (<= 4095) and the 2-D intermediate (< 2^15, convolve.c:96,
+// 149-174) fit a signed halfword, so one IDP.2A does two taps:
+//   horizontal stage: a lane produces two adjacent outputs of a row from eight aligned words (the byte
+//     parity of the row start is uniform over the warp: one funnel shift per word pair), 12 IDP.2A;
+//   the intermediate is stored TRANSPOSED (im[col][row], column pitch h + 12), so the vertical stage reads
+//     vertically adjacent values as words: a lane produces two vertically adjacent outputs from seven
+//     shared-memory words, 12 IDP.2A;
+//   vertical-only positions copy the rows transposed and use the same vertical stage.
+// Rounding and offsets are those of convolve12 above, term for term.
+#ifndef TF_CONVOLVE_PACKED
+#define TF_CONVOLVE_PACKED 1
+#endif
+__device__ __forceinline__ unsigned pack_taps(const int16_t *f, int k) {
+  return ((unsigned)f[k] & 0xffu) | (((unsigned)f[k + 1] & 0xffu) << 8);
+}
+__device__ __noinline__ void convolve12_packed(const KParams &P, const uint16_t *src, int ss, uint16_t *dst, int ds, int w,
+                                               int h, int sx, int sy, int16_t *im) {
+  const int lane = lane_id();
+  const int pbd = P.bit_depth;
+  int r0b = 3, r1b = 11;  // get_conv_params_no_round (convolve.h:63-95)
+  if (P.bit_depth + 7 - r0b + 2 > 16) {
+    const int d = P.bit_depth + 7 - r0b + 2 - 16;
+    r0b += d;
+    r1b -= d;
+  }
+  const int PT = h + 12;  // column pitch of the transposed intermediate (even: columns start word-aligned)
+  {
+    // stage A
+    const int ppr = w >> 1, rpi = 32 / ppr;  // column pairs per row, rows per iteration
+    const int pc = lane % ppr, ry = lane / ppr;
+    const int nrows = sy ? h + 11 : h;
+    const uint16_t *base = src - (sy ? 5 * ss : 0);
+    if (sx) {
+      unsigned tx[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) tx[k] = pack_taps(c_k12[sx], 2 * k);
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(base + 2 * pc - 5);
+      const unsigned sh = (a0 & 2) ? 16u : 0u;  // uniform: the pitch and 2 * pc are even
+      const unsigned char *row0 = reinterpret_cast<const unsigned char *>(a0 & ~(uintptr_t)3);
+      const int off = 1 << (pbd + 6), bits = 7 - r0b;
+#pragma unroll 1
+      for (int y = ry; y < nrows; y += rpi) {
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(row0 + (size_t)y * ss * 2);
+        uint32_t wv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) wv[k] = __ldg(wp + k);
+        unsigned pr[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) pr[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+        int s0 = 0, s1 = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          s0 = __dp2a_lo((int)pr[k], (int)tx[k], s0);
+          s1 = __dp2a_lo((int)__funnelshift_r(pr[k], pr[k + 1], 16), (int)tx[k], s1);
+        }
+        if (sy) {
+          im[(2 * pc) * PT + y] = (int16_t)rpot(s0 + off, r0b);
+          im[(2 * pc + 1) * PT + y] = (int16_t)rpot(s1 + off, r0b);
+        } else {
+          dst[y * ds + 2 * pc] = (uint16_t)clip_px(rpot(rpot(s0, r0b), bits), pbd);
+          dst[y * ds + 2 * pc + 1] = (uint16_t)clip_px(rpot(rpot(s1, r0b), bits), pbd);
+        }
+      }
+    } else {  // vertical only: the source rows, transposed
+#pragma unroll 1
+      for (int y = ry; y < nrows; y += rpi) {
+        im[(2 * pc) * PT + y] = (int16_t)__ldg(base + y * ss + 2 * pc);
+        im[(2 * pc + 1) * PT + y] = (int16_t)__ldg(base + y * ss + 2 * pc + 1);
+      }
+    }
+  }
+  __syncwarp();
+  if (!sy) return;
+  {
+    // stage B
+    unsigned ty[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) ty[k] = pack_taps(c_k12[sy], 2 * k);
+    const int col = lane % w, ypl = lane / w, ypi = 32 / w;
+    const int ob = pbd + 14 - r0b, bits = 14 - r0b - r1b;
+    const int sub = (1 << (ob - r1b)) + (1 << (ob - r1b - 1));
+#pragma unroll 1
+    for (int yp = ypl; yp < (h >> 1); yp += ypi) {
+      const uint32_t *cp = reinterpret_cast<const uint32_t *>(im + col * PT) + yp;
+      uint32_t pv[7];
+#pragma unroll
+      for (int k = 0; k < 7; k++) pv[k] = cp[k];
+      int s0 = 0, s1 = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        s0 = __dp2a_lo((int)pv[k], (int)ty[k], s0);
+        s1 = __dp2a_lo((int)__funnelshift_r(pv[k], pv[k + 1], 16), (int)ty[k], s1);
+      }
+      int v0, v1;
+      if (sx) {
+        v0 = rpot(rpot(s0 + (1 << ob), r1b) - sub, bits);
+        v1 = rpot(rpot(s1 + (1 << ob), r1b) - sub, bits);
+      } else {
+        v0 = rpot(s0, 7);
+        v1 = rpot(s1, 7);
+      }
+      dst[(2 * yp) * ds + col] = (uint16_t)clip_px(v0, pbd);
+      dst[(2 * yp + 1) * ds + col] = (uint16_t)clip_px(v1, pbd);
+    }
+  }
+  __syncwarp();
+}
+
 // The filter kernel runs FILT_WARPS = 4 warps per 32x32 block: warp q builds the predictor of
 // sub-block q of every plane (its own MV), the element-wise stages stride over all threads.
+#ifndef TF_FILT_MINB
+#define TF_FILT_MINB 6
+#endif
 constexpr int FILT_WARPS = 4;
 constexpr int FILT_THREADS = FILT_WARPS * 32;
 
@@ -1458,8 +1575,13 @@ __device__ void build_predictor(const KParams &P, const T *const ref[3], int mb_
     pos_y = iclamp(pos_y, top, (P.aligned_h[k] + 4) << 10);
     pos_x = iclamp(pos_x, left, (P.aligned_w[k] + 4) << 10);
     const T *src = ref[plane] + (pos_y >> 10) * P.pitch[k] + (pos_x >> 10);
-    convolve12<T>(P, src, P.pitch[k], &pred[plane_offset + i * plane_w + j], plane_w, w, h, (pos_x & 1023) >> 6,
-                  (pos_y & 1023) >> 6, im);
+    const int sxp = (pos_x & 1023) >> 6, syp = (pos_y & 1023) >> 6;
+    if constexpr (TF_CONVOLVE_PACKED && sizeof(T) == 2) {
+      if (sxp | syp) convolve12_packed(P, src, P.pitch[k], &pred[plane_offset + i * plane_w + j], plane_w, w, h, sxp, syp, im);
+      else convolve12<T>(P, src, P.pitch[k], &pred[plane_offset + i * plane_w + j], plane_w, w, h, 0, 0, im);
+    } else {
+      convolve12<T>(P, src, P.pitch[k], &pred[plane_offset + i * plane_w + j], plane_w, w, h, sxp, syp, im);
+    }
     plane_offset += plane_h * plane_w;
   }
   __syncthreads();
@@ -1467,94 +1589,102 @@ __device__ void build_predictor(const KParams &P, const T *const ref[3], int mb_
 
 // ---------------------------------------------------------------------------
 // Weights: av1_apply_temporal_filter_c (temporal_filter.c:557-707)
-// sq:   warp-private u32[1024] (squared differences, then horizontal 5-sums)
-// lsum: warp-private u32[1024] (co-located luma squared-difference sums)
+// sq:   block-shared u32[1024] (horizontal 5-sums of the squared differences of the current plane)
+// lsum: block-shared u32[1024] (raw luma squared differences, read by the chroma planes)
+//
+// Every thread owns the same pixels in every stage: pixel idx = tid + k * NT of a plane, i.e. column
+// j = tid % w and rows r0 + k * (NT / w).  The lanes of a row are adjacent lanes of one warp (w = 32:
+// the warp, w = 16: a half warp), so the horizontal 5-sum with edge clamp (:463-493 window, clamped as
+// the reference clamps the coordinates) is four shuffles, the vertical one five conflict-free shared
+// loads of a column, and the co-located luma sums of the chroma planes stay in registers.
+//
+// The weight (int)(exp(-scaled_error) * 1000) (:691-693) is computed in fp64 with the reference's
+// operation order.  (An fp32 ex2.approx fast path with an exact fp64 fallback near integer boundaries was
+// measured: 10 % fewer instructions in this kernel, no gain in time -- the kernel is bound by shared-memory
+// / L1 wavefronts and latency, not by the fp64 pipe -- so the single exact path stays.)
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ int tf_weight(double scaled_error) {
+  return (int)__dmul_rn(exp(-scaled_error), 1000.0);
+}
+
 template <typename T>
 __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row, int mb_col, const MV2 *mvs,
                              const int *mses, const T *pred, uint32_t *accum, uint16_t *count, uint32_t *sq,
-                             uint32_t *lsum) {
+                             uint32_t *lsum, const double *terms /* shared: d_factor[4], block_error * inv_factor [4] */) {
   constexpr int NT = FILT_THREADS;
-  const int tid = threadIdx.x;
+  constexpr int MAXPX = 1024 / NT;  // pixels of one plane per thread
+  const int tid = threadIdx.x, lane = tid & 31;
   const double inv_factor = 1.0 / ((5 + 1) * 20);
   const double weight_factor = (double)5 * inv_factor;
-  double d_factor[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const double distance = sqrt((double)(mvs[i].row * mvs[i].row + mvs[i].col * mvs[i].col));
-    const double d = distance / P.dist_thr;
-    d_factor[i] = d > 1.0 ? d : 1.0;
-  }
+  (void)mvs;
+  (void)mses;
+  (void)inv_factor;
+  uint32_t lsub[MAXPX];  // chroma: sums of the co-located luma squares of this thread's pixels
   int plane_offset = 0;
   for (int plane = 0; plane < P.num_planes; plane++) {
     const int ssy = plane ? P.ss_y : 0, ssx = plane ? P.ss_x : 0;
     const int h = 32 >> ssy, w = 32 >> ssx, n = h * w, wsh = 5 - ssx;
+    const int rpp = NT >> wsh;    // rows per pass over the plane
+    const int npass = n / NT;     // 8 (32x32), 4 (16x32), 2 (16x16)
+    const int j = tid & (w - 1), r0 = tid >> wsh;
     const int st = P.pitch[plane > 0];
     const T *src = cur[plane] + mb_row * h * st + mb_col * w;
     const int num_ref_pixels = 25 + (plane ? (1 << (ssx + ssy)) : 0);
     const double inv_num_ref_pixels = 1.0 / num_ref_pixels;
-    if (plane == 1) {  // compute_luma_sq_error_sum (:507-522); lsum still holds the raw luma squares
-      for (int idx = tid; idx < n; idx += NT) {
-        const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
-        uint32_t s = 0;
-        for (int ii = 0; ii < (1 << ssy); ii++)
-          for (int jj = 0; jj < (1 << ssx); jj++) s += lsum[((i << ssy) + ii) * 32 + (j << ssx) + jj];
-        sq[idx] = s;  // staged in sq, copied back below
-      }
-      __syncthreads();
-      for (int idx = tid; idx < n; idx += NT) lsum[idx] = sq[idx];
-      __syncthreads();
-    }
-    // compute_square_diff (:463-493)
-    for (int idx = tid; idx < n; idx += NT) {
-      const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
-      const int d = (int)__ldg(src + i * st + j) - (int)pred[plane_offset + idx];
-      const uint32_t v = (uint32_t)(d * d);
-      sq[idx] = v;
-      if (plane == 0 && P.num_planes > 1) lsum[idx] = v;
-    }
-    __syncthreads();
-    // horizontal 5-sums with edge clamp, in place: every thread reads its samples' neighbourhoods
-    // first, the block synchronises, then the sums replace the squares
-    {
-      uint32_t hs[1024 / NT];
+    // lanes holding the horizontal neighbours of this pixel's row, edge-clamped
+    const int seg = lane & ~(w - 1);
+    const int l_m2 = seg + imax(j - 2, 0), l_m1 = seg + imax(j - 1, 0);
+    const int l_p1 = seg + imin(j + 1, w - 1), l_p2 = seg + imin(j + 2, w - 1);
+    if (plane == 1) {  // compute_luma_sq_error_sum (:507-522); lsum holds the raw luma squares
 #pragma unroll
-      for (int k = 0; k < 1024 / NT; k++) {
-        const int idx = tid + k * NT;
-        hs[k] = 0;
-        if (idx < n) {
-          const int i = idx >> wsh, col = idx & (w - 1);
-#pragma unroll
-          for (int dj = -2; dj <= 2; dj++) hs[k] += sq[i * w + iclamp(col + dj, 0, w - 1)];
+      for (int k = 0; k < MAXPX; k++) {
+        if (k < npass) {
+          const int i = r0 + k * rpp;
+          uint32_t s = 0;
+          for (int ii = 0; ii < (1 << ssy); ii++)
+            for (int jj = 0; jj < (1 << ssx); jj++) s += lsum[((i << ssy) + ii) * 32 + (j << ssx) + jj];
+          lsub[k] = s;
         }
       }
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 1024 / NT; k++) {
-        const int idx = tid + k * NT;
-        if (idx < n) sq[idx] = hs[k];
-      }
-      __syncthreads();
     }
-    for (int idx = tid; idx < n; idx += NT) {
-      const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
-      // 25 (+4) squares of at most 4095^2: fits 32 bits
-      uint32_t sum_square_diff = 0;
+    // compute_square_diff (:463-493) + horizontal 5-sums
 #pragma unroll
-      for (int di = -2; di <= 2; di++) sum_square_diff += sq[iclamp(i + di, 0, h - 1) * w + j];
-      if (plane) sum_square_diff += lsum[idx];
-      if (P.bit_depth > 8) sum_square_diff >>= ((P.bit_depth - 8) * 2);
-      const double window_error = __dmul_rn((double)sum_square_diff, inv_num_ref_pixels);
-      const int sb = (i >= h / 2) * 2 + (j >= w / 2);
-      const double block_error = (double)mses[sb];
-      const double combined_error =
-          __dadd_rn(__dmul_rn(weight_factor, window_error), __dmul_rn(block_error, inv_factor));
-      double scaled_error = __dmul_rn(__dmul_rn(combined_error, d_factor[sb]), P.decay[plane]);
-      scaled_error = scaled_error < 7.0 ? scaled_error : 7.0;
-      const int weight = (int)__dmul_rn(exp(-scaled_error), 1000.0);
-      const int pidx = plane_offset + idx;
-      accum[pidx] += (uint32_t)(weight * (int)pred[pidx]);
-      count[pidx] = (uint16_t)(count[pidx] + weight);
+    for (int k = 0; k < MAXPX; k++) {
+      if (k < npass) {
+        const int i = r0 + k * rpp, idx = tid + k * NT;  // == i * w + j
+        const int d = (int)__ldg(src + i * st + j) - (int)pred[plane_offset + idx];
+        const uint32_t v = (uint32_t)(d * d);
+        if (plane == 0 && P.num_planes > 1) lsum[idx] = v;
+        const uint32_t h5 = v + __shfl_sync(FULL, v, l_m2) + __shfl_sync(FULL, v, l_m1) + __shfl_sync(FULL, v, l_p1) +
+                            __shfl_sync(FULL, v, l_p2);
+        sq[idx] = h5;
+      }
+    }
+    __syncthreads();
+    const int hbd_sh = P.bit_depth > 8 ? (P.bit_depth - 8) * 2 : 0;
+    const int sb_col = (j >= w / 2);
+    // a thread's pixels lie in one column half, i.e. in two sub-blocks: the upper and the lower one
+    const double d_factor[2] = { terms[sb_col], terms[2 + sb_col] };
+    const double b_term[2] = { terms[4 + sb_col], terms[6 + sb_col] };
+#pragma unroll
+    for (int k = 0; k < MAXPX; k++) {
+      if (k < npass) {
+        const int i = r0 + k * rpp, idx = tid + k * NT;
+        // 25 (+4) squares of at most 4095^2: fits 32 bits
+        uint32_t sum_square_diff = sq[imax(i - 2, 0) * w + j] + sq[imax(i - 1, 0) * w + j] + sq[idx] +
+                                   sq[imin(i + 1, h - 1) * w + j] + sq[imin(i + 2, h - 1) * w + j];
+        if (plane) sum_square_diff += lsub[k];
+        sum_square_diff >>= hbd_sh;
+        const double window_error = __dmul_rn((double)sum_square_diff, inv_num_ref_pixels);
+        const int sb = (i >= h / 2);  // rows ascend with k: the first half of the passes is the upper sub-block
+        const double combined_error = __dadd_rn(__dmul_rn(weight_factor, window_error), b_term[sb]);
+        double scaled_error = __dmul_rn(__dmul_rn(combined_error, d_factor[sb]), P.decay[plane]);
+        scaled_error = scaled_error < 7.0 ? scaled_error : 7.0;
+        const int weight = tf_weight(scaled_error);
+        const int pidx = plane_offset + idx;
+        accum[pidx] += (uint32_t)(weight * (int)pred[pidx]);
+        count[pidx] = (uint16_t)(count[pidx] + weight);
+      }
     }
     __syncthreads();
     plane_offset += n;
@@ -1572,19 +1702,21 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
 //   pred (T view of u16[num_pels]) | im i16[FILT_WARPS][27*16] | red u64[FILT_WARPS]
 // ---------------------------------------------------------------------------
 struct WarpSmem {
+  double *terms;  // per frame: d_factor of the four sub-blocks, then block_error * inv_factor
   uint32_t *accum, *sq, *lsum;
   uint16_t *count, *pred;
   int16_t *im;
   unsigned long long *red;
 };
-constexpr int FILT_IM = (16 + 11) * 16;  // intermediate rows of one 2-D 12-tap sub-block
+constexpr int FILT_IM = (16 + 12) * 16;  // intermediate of one 2-D 12-tap sub-block (transposed form: 16 columns of pitch 28)
 __host__ __device__ inline size_t filter_smem_bytes(int num_pels) {
-  return (size_t)num_pels * 8 + 2 * 1024 * 4 + FILT_WARPS * FILT_IM * 2 + FILT_WARPS * 8;
+  return (size_t)num_pels * 8 + 2 * 1024 * 4 + FILT_WARPS * FILT_IM * 2 + FILT_WARPS * 8 + 8 * 8;
 }
 __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels) {
   WarpSmem sm;
   sm.red = reinterpret_cast<unsigned long long *>(raw);
-  sm.accum = reinterpret_cast<uint32_t *>(sm.red + FILT_WARPS);
+  sm.terms = reinterpret_cast<double *>(sm.red + FILT_WARPS);
+  sm.accum = reinterpret_cast<uint32_t *>(sm.terms + 8);
   sm.sq = sm.accum + num_pels;
   sm.lsum = sm.sq + 1024;
   sm.count = reinterpret_cast<uint16_t *>(sm.lsum + 1024);
@@ -1594,7 +1726,7 @@ __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels)
 }
 
 template <typename T>
-__global__ void __launch_bounds__(FILT_THREADS, 6) tf_filter_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(FILT_THREADS, TF_FILT_MINB) tf_filter_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = FILT_THREADS;
   const WarpSmem sm = carve_smem(smem_raw, P.num_pels);
@@ -1667,6 +1799,12 @@ __global__ void __launch_bounds__(FILT_THREADS, 6) tf_filter_kernel(const __grid
         }
       }
     }
+    if (tid < 4) {  // the distance and block-error terms of the weight (temporal_filter.c:616-625,676-678), once per frame
+      const double distance = sqrt((double)(sub_mvs[tid].row * sub_mvs[tid].row + sub_mvs[tid].col * sub_mvs[tid].col));
+      const double d = distance / P.dist_thr;
+      sm.terms[tid] = d > 1.0 ? d : 1.0;
+      sm.terms[4 + tid] = __dmul_rn((double)sub_mses[tid], 1.0 / ((5 + 1) * 20));
+    }
     build_predictor<T>(P, ref, mb_row, mb_col, sub_mvs, pred, sm.im + (tid >> 5) * FILT_IM);
     if (P.d_mvs && tid == 0) {
 #pragma unroll
@@ -1681,7 +1819,7 @@ __global__ void __launch_bounds__(FILT_THREADS, 6) tf_filter_kernel(const __grid
     }
     if (P.d_pred)
       for (int i = tid; i < P.num_pels; i += NT) P.d_pred[bf * P.num_pels + i] = (uint16_t)pred[i];
-    apply_filter<T>(P, cur, mb_row, mb_col, sub_mvs, sub_mses, pred, sm.accum, sm.count, sm.sq, sm.lsum);
+    apply_filter<T>(P, cur, mb_row, mb_col, sub_mvs, sub_mses, pred, sm.accum, sm.count, sm.sq, sm.lsum, sm.terms);
   }
 
   // tf_normalize_filtered_frame (:740-777); OD_DIVU == integer division here

@@ -43,7 +43,22 @@ WORKLOADS = {
     "1080p8_n7": (1920, 1080, 8, 7, 4),
     "cif8_n7": (352, 288, 8, 7, 5),
 }
-Q_FACTOR = 32  # av1_get_q() of a mid-quality ARF; held fixed so runs are comparable
+# Window parameters as aomenc itself passes them (profiles/aomenc_e2e_r02.json: TF_SEAM_WINDOW lines of the
+# CONFIG_TF_GPU build on the same synthetic clips, --end-usage=q --cq-level=32): q_factor of the ARF window,
+# allow_high_precision_mv = 1; the noise levels are estimated from the frame to filter in every run.
+Q_FACTOR = 43
+ALLOW_HP = 1
+SPEED_CLASS = "good cpu-used=4 (PRUNED_MORE, prune mesh lvl2, skip-row SAD >= 720p)"
+
+
+def workload_config(wl):
+    """The `config` object of the JSON line: names the workload only, identical in the tfgpu and reference arms."""
+    width, height, bd, n, strength = WORKLOADS[wl]
+    return {"workload": wl, "width": width, "height": height, "bit_depth": bd, "chroma": "4:2:0", "num_frames": n,
+            "filter_strength": strength, "q_factor": Q_FACTOR, "allow_hp": ALLOW_HP, "speed_class": SPEED_CLASS,
+            "clip": "synthetic moving texture (tests/_clips.py), seeded",
+            "l2": f"inputs larger than L2: one window = {plane_bytes(width, height, bd) * n / 1e6:.0f} MB, "
+                  "several windows cycled"}
 
 
 def load_package():
@@ -71,6 +86,13 @@ def plane_bytes(width, height, bd):
 # ---------------------------------------------------------------------------------------
 # INT roofline: scalar-equivalent pixel operations per (block, reference frame)
 # ---------------------------------------------------------------------------------------
+def window_params(wl):
+    import _params
+    width, height, bd, n, strength = WORKLOADS[wl]
+    return _params.tf_params(width, height, n, bit_depth=bd, q_factor=Q_FACTOR, filter_strength=strength,
+                             allow_hp=ALLOW_HP)
+
+
 def int_work_per_block_ref(allow_hp):
     sad = 141 * (512 + 4 * 128)              # 1x32x32 + 4x16x16 searches, 141 sites each, skip-row SAD
     var = 2 * 2048                           # full-pel variance re-scores
@@ -233,7 +255,7 @@ def run_reference_arm(args, wl):
     import _params
     width, height, bd, n, strength = WORKLOADS[wl]
     frames = make_window(width, height, bd, n, seed=77 if bd > 8 else 1234)
-    p = _params.tf_params(width, height, n, bit_depth=bd, q_factor=Q_FACTOR, filter_strength=strength)
+    p = window_params(wl)
     cls, kind, simd = cpu_filter_class(args.ref_simd)
     filt = cls(p, frames)
     p["noise_levels"] = tuple(filt.estimate_noise())
@@ -282,8 +304,8 @@ def run_reference_arm(args, wl):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps / frac,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u16" if bd > 8 else "u8", "data": "synthetic",
-        "config": {"workload": wl, "width": width, "height": height, "bit_depth": bd, "num_frames": n,
-                   "speed_class": "good cpu-used=4", "note": "ms_per_step is per whole frame (sample time / sampled fraction)"},
+        "config": workload_config(wl),
+        "measurement": {"note": "ms_per_step is per whole frame (sample time / sampled fraction)"},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": nw, "kind": kind, "simd": simd,
                          "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -355,6 +377,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     pkg = load_package()
+    import importlib
+    sharding = importlib.import_module("aom_av1_psy_b200.sharding")
     width, height, bd, n, strength = WORKLOADS[wl]
     slab_req = args.mode == "slab" and world > 1
     conc = args.concurrent if args.concurrent > 0 else (1 if slab_req else (2 if width >= 3000 else 4))
@@ -363,7 +387,7 @@ def main():
 
     use_hbd = bd > 8
     mb_rows, mb_cols = (height + 31) // 32, (width + 31) // 32
-    p = _params.tf_params(width, height, n, bit_depth=bd, q_factor=Q_FACTOR, filter_strength=strength)
+    p = window_params(wl)
 
     # windows resident on this GPU: enough distinct data to exceed L2 (126 MB) several times
     win_bytes = plane_bytes(width, height, bd) * n
@@ -401,9 +425,7 @@ def main():
                 ctxs[ci].cache_frame(b)
 
     if slab:
-        r0 = (mb_rows * rank) // world
-        r1 = (mb_rows * (rank + 1)) // world
-        p["out_row_begin"], p["out_row_end"] = r0, r1
+        p["out_row_begin"], p["out_row_end"] = sharding.slab_rows(mb_rows, world, rank)
 
     def barrier():
         for c in ctxs:
@@ -412,32 +434,13 @@ def main():
         if world > 1:
             dist.barrier()
 
-    gather_bufs = None
+    slab_win = sharding.SlabWindow(mb_rows, world, rank) if slab else None
 
     def slab_gather(diff):
         """NCCL gather of the disjoint output row slabs to rank 0 and a 16-byte all-reduce of
         FRAME_DIFF (integer sums, so order independent like ethread.c:2161-2173)."""
-        nonlocal gather_bufs
-        max_rows = max((mb_rows * (r + 1)) // world - (mb_rows * r) // world for r in range(world))
-        tensors = []
-        for pl in range(3):
-            ptr, pitch, rows, row_bytes = ctx.output_device_plane(pl)
-            bh = 32 >> (1 if pl else 0)
-
-            class _W:  # zero-copy view of the library's output plane (one spare block row fits the device border)
-                pass
-            wobj = _W()
-            wobj.__cuda_array_interface__ = {"shape": ((mb_rows + 1) * bh * pitch,), "typestr": "|u1",
-                                             "data": (ptr, False), "version": 3}
-            t = torch.as_tensor(wobj, device=f"cuda:{local}")
-            lo = (mb_rows * rank) // world * bh * pitch
-            tensors.append(t[lo:lo + max_rows * bh * pitch])
-        if gather_bufs is None:
-            gather_bufs = [[torch.empty_like(t) for _ in range(world)] if rank == 0 else None for t in tensors]
-        for t, g in zip(tensors, gather_bufs):
-            dist.gather(t, g, dst=0)
         d = torch.from_numpy(diff.copy()).to(f"cuda:{local}")
-        dist.all_reduce(d)
+        slab_win.gather(slab_win.device_slabs(ctx, torch, f"cuda:{local}"), d, dist, torch)
         torch.cuda.current_stream().synchronize()
 
     ids = [[b.frame_id for b in bufs] for _, bufs in windows]
@@ -499,6 +502,104 @@ def main():
     frames_done = args.steps * (1 if slab else world * conc)
     value = frames_done / (tot_ms * 1e-3)
 
+    # ---- the timed configuration is verified: the frame every context produced last, with all contexts in
+    # flight, must equal the same window filtered synchronously on an otherwise idle device --------------
+    import hashlib
+    vout = pkg.Yv12Buffer(width, height, 1, 1, use_hbd, p["border"])
+
+    def out_hash(c):
+        c.download_output(vout)
+        h = hashlib.sha256()
+        for pl in range(3):
+            h.update(np.ascontiguousarray(vout.full_blocks(pl)).tobytes())
+        return h.hexdigest()
+
+    verified = None
+    if not slab:
+        last_w = (args.steps - 1) % nwin
+        timed_hashes = [out_hash(c) for c in ctxs]
+        sync_hashes = []
+        for c in ctxs:
+            c.filter_resident(p, ids[last_w])
+            sync_hashes.append(out_hash(c))
+        vt = torch.tensor([1.0 if timed_hashes == sync_hashes else 0.0], device=f"cuda:{local}", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(vt, op=dist.ReduceOp.MIN)
+        verified = bool(vt.item() == 1.0)
+
+    # ---- 4K on several GPUs: the slab-parallel partitioning of ONE window (BASELINE.json config 4), measured
+    # in the same run as the window-parallel line and reported in its "slab" object ---------------------
+    def measure_slab(nsteps):
+        dev = f"cuda:{local}"
+        sw = sharding.SlabWindow(mb_rows, world, rank)
+        frames = make_window(width, height, bd, n, 77 if bd > 8 else 1234)  # the same pixels on every rank
+        sids = []
+        for i, (y, u, v) in enumerate(frames):
+            b = pkg.Yv12Buffer(width, height, 1, 1, use_hbd, p["border"], frame_id=9000 + i)
+            ctx.cache_frame(b.set_planes(y, u, v, extend=False))
+            sids.append(b.frame_id)
+        pf = dict(p, out_row_begin=0, out_row_end=0)
+        # one whole window on one GPU, nothing else in flight: the latency strong scaling is measured against
+        for _ in range(3):
+            ctx.filter_resident(pf, sids)
+        barrier()
+        ctx.event_record(2)
+        for _ in range(nsteps):
+            ctx.filter_resident(pf, sids)
+        ctx.event_record(3)
+        t_one = ctx.event_elapsed_ms(2, 3) / nsteps
+        full_diff = ctx.filter_resident(pf, sids)[1]
+        ctx.download_output(vout)
+        full_planes = [vout.full_blocks(pl).copy() for pl in range(3)]
+        ps = sw.params(p)
+        gather_ms = [0.0]
+        chain_ms = [0.0]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        last = {}
+
+        def step():
+            ctx.filter_resident_async(ps, sids)
+            _, diff = ctx.filter_resident_result()
+            chain_ms[0] += ctx.last_kernel_times()[0]
+            d = torch.from_numpy(diff.copy()).to(dev)
+            ev[0].record()
+            g, dsum = sw.gather(sw.device_slabs(ctx, torch, dev), d, dist, torch)
+            ev[1].record()
+            torch.cuda.current_stream().synchronize()
+            gather_ms[0] += ev[0].elapsed_time(ev[1])
+            last["g"], last["d"] = g, dsum
+
+        for _ in range(3):
+            step()
+        smp = ClockSampler(local)
+        barrier()
+        smp.start()
+        gather_ms[0] = chain_ms[0] = 0.0
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            step()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3 / nsteps
+        clk = smp.stop()
+        t = torch.tensor([wall, t_one, gather_ms[0] / nsteps, chain_ms[0] / nsteps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, t_one_max, g_ms, c_ms = t.tolist()
+        ok = None
+        if rank == 0:  # the gathered frame against this GPU's own full-frame result
+            pitches = [ctx.output_device_plane(pl)[1] for pl in range(3)]
+            planes = sw.assemble(last["g"], pitches, torch.cat)
+            ok = bool((last["d"].cpu().numpy() == full_diff).all())
+            for pl in range(3):
+                want = full_planes[pl]
+                got = planes[pl][:, :want.shape[1] * want.itemsize].cpu().numpy().view(want.dtype)
+                ok = ok and bool((got == want).all())
+        return {"mode": "block-row slabs of one window per GPU + NCCL gather to rank 0 (SlabWindow)",
+                "ms_per_frame": wall, "frames_per_sec": 1e3 / wall, "single_gpu_ms_per_frame": t_one_max,
+                "speedup": t_one_max / wall, "efficiency": t_one_max / wall / world,
+                "gather_ms": g_ms, "search32_chain_ms": c_ms, "steps": nsteps, "clocks": clk, "verified": ok,
+                "limiter": "the ref_mv chain: one tf_search32 launch per reference frame whose per-block latency "
+                           "does not shrink with the number of block rows"}
+
     # executed work of one window (untimed, instrumented): SURVEY 8d "executed op count"
     ctx.collect_counters(1)
     ctx.filter_resident(p, ids[0])
@@ -555,6 +656,10 @@ def main():
         e2e = {"value": args.steps * world * conc / (te.item() * 1e-3), "unit": "frames/s",
                "h2d_bytes_per_step": plane_bytes(width, height, bd) * n * conc, "d2h_bytes_per_step": int(d2h) * conc}
 
+    slab_section = None
+    if world > 1 and not slab and width >= 3000:
+        slab_section = measure_slab(max(args.steps, 30))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -600,19 +705,24 @@ def main():
     t_exec = nbr * (w_exec["sad"] / r_sad + (w_exec["var"] + w_exec["subpel"] + w_exec["pred"]) / rates["imad"]
                     + w_exec["weights"] / rates["iadd"]) / 1e9
     exec_info = {"work_per_block_ref": w_exec, "t_int_ms": t_exec * conc * 1e3, "frac": t_exec * conc / kern_s}
+    # px-ops of the whole step / time: the binding (integer) roofline at top level, the HBM view nested
+    w_step = sum(W.values()) * mb_rows * mb_cols * (n - 1) * rows_frac * conc
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "traffic": traffic, "peak_source": peak_src, "kernel": dom_name, "kernel_ms": per_launch_ms[dom_name],
+        "bound": "int", "achieved": w_step / kern_s / 1e9, "peak": w_step / (t_int * conc) / 1e9, "unit": "Gpixel-op/s",
+        "frac": t_int * conc / kern_s, "traffic": traffic,
+        "note": "binding roofline per SURVEY 8d: T_int = sum_class W_class / R_class over pipe rates measured in this run "
+                "(tf_gpu_microbench), whole step (all windows in flight); frac = T_int / T_step.  W = static-content floor "
+                "per (block, reference frame); `executed` = instrumented counts of this clip",
+        "kernel": dom_name, "kernel_ms": per_launch_ms[dom_name],
         "launches_per_step": {"tf_search32_kernel": nref, "tf_search16_kernel": nref, "tf_filter_kernel": 1},
-        "algorithmic_bytes_per_launch": alg_bytes[dom_name],
         "phases_ms": {"search32_chain_with_search16_overlapped": kt[0], "search16_tail": kt[1], "filter": kt[2]},
-        "step": {"algorithmic_bytes": step_alg, "kernels_ms_sum": kern_s * 1e3,
-                 "achieved_gbs": step_alg / kern_s / 1e9, "frac": step_alg / kern_s / 1e9 / hbm_peak},
-        "int": {"note": "binding roofline per SURVEY 8d: T_int = sum_class W_class / R_class over measured pipe rates, whole "
-                        "step (all windows in flight); W = static-content floor, executed = instrumented counts of this clip",
-                "work_per_block_ref": W, "rates_giga_lane_ops_per_s": rates, "t_int_ms": t_int * conc * 1e3,
-                "frac": t_int * conc / kern_s,
-                "executed": exec_info},
+        "work_per_block_ref": W, "rates_giga_lane_ops_per_s": rates, "t_int_ms": t_int * conc * 1e3,
+        "executed": exec_info,
+        "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "peak_source": peak_src, "kernel": dom_name, "algorithmic_bytes_per_launch": alg_bytes[dom_name],
+                "traffic_bytes_per_launch": traffic,
+                "step": {"algorithmic_bytes": step_alg, "kernels_ms_sum": kern_s * 1e3,
+                         "achieved_gbs": step_alg / kern_s / 1e9, "frac": step_alg / kern_s / 1e9 / hbm_peak}},
     }
 
     line = {
@@ -620,15 +730,16 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if slab else "weak", "vs_baseline": None, "dtype": "u16" if use_hbd else "u8",
         "data": "synthetic",
-        "config": {"workload": wl, "width": width, "height": height, "bit_depth": bd, "chroma": "4:2:0",
-                   "num_frames": n, "filter_strength": strength, "q_factor": Q_FACTOR,
-                   "speed_class": "good cpu-used=4 (PRUNED_MORE, prune mesh lvl2, skip-row SAD)",
-                   "mode": "slab rows + NCCL gather" if slab else "independent windows per GPU",
-                   "windows_in_flight_per_gpu": conc,
-                   "l2": f"inputs larger than L2: {nwin} resident windows x {win_bytes / 1e6:.0f} MB cycled",
-                   "timing": "CUDA events on the library stream around K steps, max over ranks"},
+        "config": workload_config(wl),
+        "measurement": {"mode": "slab rows + NCCL gather" if slab else "independent windows per GPU",
+                        "windows_in_flight_per_gpu": conc,
+                        "resident_windows_cycled": f"{nwin} per context x {win_bytes / 1e6:.0f} MB",
+                        "timing": "CUDA events on the library stream around K steps, max over ranks"},
+        "verified": verified,
         "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
     }
+    if slab_section:
+        line["slab"] = slab_section
     if e2e:
         line["e2e"] = e2e
     if not args.no_cpu_baseline and world == 1:

@@ -41,14 +41,14 @@ def test_concurrent_contexts_equal_the_synchronous_call(pkg, case):
     mb_rows = (H + 31) // 32
 
     # the synchronous public call, one window at a time on an idle device: the expected frames
-    sync = pkg.TemporalFilterGpu(max_cached_frames=24)
     want = {}
     for ci in range(K):
+        sync = pkg.TemporalFilterGpu(max_cached_frames=24)  # per window set: the frame ids repeat across contexts
         for w in range(nwin):
             out = pkg.Yv12Buffer(W, H, 1, 1, bd > 8, p["border"])
             r = sync.temporal_filter(p, [b for b in wins[ci][w][1]], out)
             want[ci, w] = ([out.full_blocks(pl).copy() for pl in range(3)], r["diff"].copy())
-    sync.close()
+        sync.close()
 
     # the oracle on one block row of one window pins the expected frames themselves
     o = _oracle.OracleFilter(p, wins[K - 1][nwin - 1][0])
