@@ -31,7 +31,7 @@ EXPORTS = [
     "tf_gpu_evict_frame", "tf_gpu_filter_resident", "tf_gpu_download_output", "tf_gpu_output_device_plane",
     "tf_gpu_host_register", "tf_gpu_host_unregister", "tf_gpu_last_stats", "tf_gpu_event_record",
     "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench", "tf_gpu_last_kernel_times", "tf_gpu_filter_resident_async", "tf_gpu_filter_resident_result", "tf_gpu_collect_counters", "tf_gpu_read_counters",
-    "tf_gpu_cache_frame_async", "tf_gpu_debug_read_plane", "tf_gpu_device_border",
+    "tf_gpu_cache_frame_async", "tf_gpu_debug_read_plane", "tf_gpu_device_border", "tf_gpu_fullpel_search_batch",
 ]
 
 
@@ -68,6 +68,14 @@ class Params(C.Structure):
     ]
 
 
+class SearchItem(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("start_row", C.c_int16), ("start_col", C.c_int16)]
+
+
+class SearchResult(C.Structure):
+    _fields_ = [("row", C.c_int16), ("col", C.c_int16), ("var", C.c_int32)]
+
+
 class Dump(C.Structure):
     _fields_ = [("subblock_mvs", C.c_void_p), ("subblock_mses", C.c_void_p), ("pred", C.c_void_p),
                 ("accum", C.c_void_p), ("count", C.c_void_p)]
@@ -101,6 +109,8 @@ def load_library():
     lib.tf_gpu_cache_frame_async.argtypes = [vp, C.POINTER(Frame)]
     lib.tf_gpu_debug_read_plane.argtypes = [vp, u64, i, vp, i, i, i, i, i]
     lib.tf_gpu_device_border.restype = i
+    lib.tf_gpu_fullpel_search_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(Frame), C.POINTER(Frame), i,
+                                                C.POINTER(SearchItem), i, C.POINTER(SearchResult)]
     lib.tf_gpu_filter_resident.argtypes = [vp, C.POINTER(Params), C.POINTER(u64), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_float)]
     lib.tf_gpu_download_output.argtypes = [vp, C.POINTER(Frame), i, i]
@@ -308,6 +318,17 @@ class TemporalFilterGpu:
         dst = np.zeros((h, w), frame.dtype)
         self._check(self.lib.tf_gpu_debug_read_plane(self.h, frame.frame_id, plane, dst.ctypes.data, w, x0, y0, w, h))
         return dst
+
+    def fullpel_search_batch(self, params, src, ref, block_size, items):
+        """items: sequence of (x, y, start_row, start_col); returns an int array [n, 3] of (row, col, var) --
+        av1_full_pixel_search() as tf_motion_search() configures it, per block (see tf_gpu.h)."""
+        cp = make_params(params) if isinstance(params, dict) else params
+        n = len(items)
+        arr = (SearchItem * max(n, 1))(*[SearchItem(*map(int, it)) for it in items])
+        res = (SearchResult * max(n, 1))()
+        cs, cr = src.c_frame(), ref.c_frame()
+        self._check(self.lib.tf_gpu_fullpel_search_batch(self.h, C.byref(cp), C.byref(cs), C.byref(cr), block_size, arr, n, res))
+        return np.array([(r.row, r.col, r.var) for r in res[:n]], np.int64).reshape(n, 3)
 
     def device_border(self):
         return self.lib.tf_gpu_device_border()

@@ -109,8 +109,8 @@ struct tf_gpu_ctx {
   int last_launches = 0;
   float last_kernel_ms = 0.f;
   // dump buffers (device), grown on demand
-  void *d_dump[10] = {};
-  size_t d_dump_sz[10] = {};
+  void *d_dump[12] = {};
+  size_t d_dump_sz[12] = {};
   char err[512] = { 0 };
 };
 
@@ -380,11 +380,9 @@ int ensure_dump(tf_gpu_ctx *ctx, int i, size_t bytes) {
   return TF_GPU_OK;
 }
 
-// Build kernel parameters and launch the block kernel over rows [rb, re).
-int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *frames, const Geometry &g,
-                  unsigned long long *d_diff, const tf_gpu_dump *dump, const CallEvents *te) {
-  const bool timed = te != nullptr;
-  KParams K;
+// Geometry, window and search parameters shared by every kernel (what tf_motion_search() and
+// av1_tf_do_filtering_row() resolve from AV1_COMP before the per-block loop).
+void fill_kparams(const tf_gpu_ctx *ctx, const tf_gpu_params *p, const Geometry &g, KParams &K) {
   memset(&K, 0, sizeof(K));
   K.width = g.crop_w[0];
   K.height = g.crop_h[0];
@@ -419,7 +417,6 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   }
   K.use_skip = p->use_downsampled_sad ? 1 : 0;
   K.compute_diff = p->compute_frame_diff ? 1 : 0;
-  const int min_frame_size = K.width < K.height ? K.width : K.height;  // av1_apply_temporal_filter_c: the source size (:603)
   // tf_motion_search() uses cm->width / cm->height (the coded size; temporal_filter.c:99-100)
   const int cm_w = p->cm_width > 0 ? p->cm_width : K.width, cm_h = p->cm_height > 0 ? p->cm_height : K.height;
   const int min_cm_size = cm_w < cm_h ? cm_w : cm_h;
@@ -436,6 +433,15 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   }
   K.mse_thresh = ((min_cm_size >= 720) ? 12 : 3) << (p->bit_depth - 8);  // temporal_filter.c:249-250
   K.hbd_shift = g.is_hbd ? (p->bit_depth == 10 ? 2 : (p->bit_depth == 12 ? 4 : 0)) : 0;
+}
+
+// Build kernel parameters and launch the block kernel over rows [rb, re).
+int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *frames, const Geometry &g,
+                  unsigned long long *d_diff, const tf_gpu_dump *dump, const CallEvents *te) {
+  const bool timed = te != nullptr;
+  KParams K;
+  fill_kparams(ctx, p, g, K);
+  const int min_frame_size = K.width < K.height ? K.width : K.height;  // av1_apply_temporal_filter_c: the source size (:603)
   {  // decay factors, temporal_filter.c:583-597 (host libm, as the reference)
     double q_decay = pow((double)p->q_factor / 20, 2);
     q_decay = q_decay < 1e-5 ? 1e-5 : (q_decay > 1 ? 1 : q_decay);
@@ -829,7 +835,7 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
   if (ctx->ev_out_done) cudaEventDestroy(ctx->ev_out_done);
   for (int p = 0; p < 3; p++)
     if (ctx->out.base[p]) cudaFree(ctx->out.base[p]);
-  for (int i = 0; i < 10; i++)
+  for (int i = 0; i < 12; i++)
     if (ctx->d_dump[i]) cudaFree(ctx->d_dump[i]);
   if (ctx->d_diff) cudaFree(ctx->d_diff);
   if (ctx->h_diff) cudaFreeHost(ctx->h_diff);
@@ -1082,6 +1088,69 @@ int tf_gpu_output_device_plane(tf_gpu_ctx *ctx, int plane, void **dptr, size_t *
   if (pitch_bytes) *pitch_bytes = (size_t)g.pitch[k] * es;
   if (rows) *rows = ((g.crop_h[0] + 31) / 32) * (32 >> (plane ? g.ss_y : 0));
   if (row_bytes) *row_bytes = (int)(((g.crop_w[0] + 31) / 32) * (32 >> (plane ? g.ss_x : 0)) * es);
+  return TF_GPU_OK;
+}
+
+int tf_gpu_fullpel_search_batch(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame *src,
+                                const tf_gpu_frame *ref, int block_size, const tf_gpu_search_item *items, int n,
+                                tf_gpu_search_result *results) {
+  if (!ctx) return TF_GPU_ERR_INVALID;
+  if (!params || !src || !ref || !items || !results) return fail(ctx, TF_GPU_ERR_INVALID, "NULL argument");
+  if (block_size != 16 && block_size != 32) return fail(ctx, TF_GPU_ERR_INVALID, "block_size must be 16 or 32");
+  if (n < 0) return fail(ctx, TF_GPU_ERR_INVALID, "negative item count");
+  if (n == 0) return TF_GPU_OK;
+  static_assert(sizeof(tf_gpu_search_item) == sizeof(SearchItem) && sizeof(tf_gpu_search_result) == sizeof(SearchResult),
+                "ABI structs and device structs must agree");
+  tf_gpu_params p = *params;  // only the search fields are read; make the window fields valid
+  p.num_frames = 2;
+  p.filter_frame_idx = 0;
+  p.num_planes = 1;
+  if (p.subpel_iters_per_step < 1) p.subpel_iters_per_step = 1;
+  int rc = validate_params(ctx, &p);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  CallScope scope(ctx);
+  ctx->last_launches = 0;
+  DevFrame *ds = nullptr, *dr = nullptr;
+  rc = get_frame(ctx, src, src->plane[1] ? 3 : 1, &ds);
+  if (rc) return rc;
+  rc = get_frame(ctx, ref, ref->plane[1] ? 3 : 1, &dr);
+  if (rc) return rc;
+  if (!(ds->g == dr->g)) return fail(ctx, TF_GPU_ERR_INVALID, "src and ref must share geometry");
+  const Geometry &g = ds->g;
+  rc = validate_geometry(ctx, &p, g);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++) {
+    const tf_gpu_search_item &it = items[i];
+    // the block starts inside the mi grid (it may stick out of it like the last 32x32 row of a 1080p frame);
+    // the SAD engine reads source rows with 16-byte loads
+    if (it.x < 0 || it.y < 0 || (it.x & 15) || (it.y & 3) || it.x >= p.mi_cols * 4 || it.y >= p.mi_rows * 4)
+      return fail(ctx, TF_GPU_ERR_INVALID, "item %d: block position (%d, %d) not supported", i, it.x, it.y);
+  }
+  KParams K;
+  fill_kparams(ctx, &p, g, K);
+  rc = ensure_dump(ctx, 10, (size_t)n * sizeof(SearchItem));
+  if (rc) return rc;
+  rc = ensure_dump(ctx, 11, (size_t)n * sizeof(SearchResult));
+  if (rc) return rc;
+  SearchItem *d_items = (SearchItem *)ctx->d_dump[10];
+  SearchResult *d_res = (SearchResult *)ctx->d_dump[11];
+  CU(cudaMemcpyAsync(d_items, items, (size_t)n * sizeof(SearchItem), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->stream, ds->ready, 0));
+  CU(cudaStreamWaitEvent(ctx->stream, dr->ready, 0));
+  if (g.is_hbd) {
+    const uint16_t *a = (const uint16_t *)ds->p00[0], *b = (const uint16_t *)dr->p00[0];
+    if (block_size == 32) tf_fullpel_batch_kernel<uint16_t, 32><<<n, 32, WIN_BYTES, ctx->stream>>>(K, a, b, d_items, d_res, n);
+    else tf_fullpel_batch_kernel<uint16_t, 16><<<n, 32, WIN16_BYTES, ctx->stream>>>(K, a, b, d_items, d_res, n);
+  } else {
+    const uint8_t *a = (const uint8_t *)ds->p00[0], *b = (const uint8_t *)dr->p00[0];
+    if (block_size == 32) tf_fullpel_batch_kernel<uint8_t, 32><<<n, 32, WIN_BYTES, ctx->stream>>>(K, a, b, d_items, d_res, n);
+    else tf_fullpel_batch_kernel<uint8_t, 16><<<n, 32, WIN16_BYTES, ctx->stream>>>(K, a, b, d_items, d_res, n);
+  }
+  CU(cudaGetLastError());
+  ctx->last_launches++;
+  CU(cudaMemcpyAsync(results, d_res, (size_t)n * sizeof(SearchResult), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return TF_GPU_OK;
 }
 

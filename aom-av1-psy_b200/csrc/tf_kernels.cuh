@@ -1273,6 +1273,10 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
 // no second partial wave forms; MINB = 12 (168 registers, no spills) for larger grids, where the
 // latency-bound chain runs faster per launch and leaves registers for concurrent 16x16 launches.
 constexpr int S32_WARPS_HI = 20, S32_WARPS_LO = 12;
+#ifndef TF_S16_WARPS
+#define TF_S16_WARPS 24
+#endif
+constexpr int S16_WARPS = TF_S16_WARPS;
 template <typename T, int MINB>
 __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1338,7 +1342,7 @@ __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_cons
 // 32x32 result (temporal_filter.c:194) and reuses the 32x32 block's MV limits
 // (:202-205).  One warp per task, frame-major task order for L2 locality.
 template <typename T>
-__global__ void __launch_bounds__(32, 24) tf_search16_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(32, S16_WARPS) tf_search16_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = lane_id();
   const int nblk = (P.row_end - P.row_begin) * P.mb_cols;
@@ -1367,6 +1371,51 @@ __global__ void __launch_bounds__(32, 24) tf_search16_kernel(const __grid_consta
     P.s_sub_mv[(bf * 4 + sub) * 2 + 0] = (int16_t)best.row;
     P.s_sub_mv[(bf * 4 + sub) * 2 + 1] = (int16_t)best.col;
     P.s_sub_mse[bf * 4 + sub] = (int)((err + 128u) / 256u);
+  }
+}
+
+// Batched full-pixel search (tf_gpu_fullpel_search_batch): one warp per item, the engine of the two
+// kernels above on an arbitrary block of an arbitrary frame pair.  MV limits for a W x W block at mi
+// position (y / 4, x / 4): av1_set_mv_{row,col}_limits (mcomp.h:216-240), then av1_set_mv_search_range
+// (mcomp.c:196-215) around a zero reference MV.
+struct SearchItem {
+  int x, y;
+  int16_t start_row, start_col;
+};
+struct SearchResult {
+  int16_t row, col;
+  int32_t var;
+};
+template <typename T, int W>
+__global__ void __launch_bounds__(32, W == 32 ? S32_WARPS_LO : 24)
+    tf_fullpel_batch_kernel(const __grid_constant__ KParams P, const T *src, const T *ref, const SearchItem *items,
+                            SearchResult *results, int n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = lane_id();
+  if ((int)blockIdx.x >= n) return;
+  const SearchItem it = items[blockIdx.x];
+  Search<T> S;
+  search_init(S, P, 0, 0);
+  const int border = P.border, mi_row = it.y >> 2, mi_col = it.x >> 2, mih = W / 4;
+  S.lim.row_min = imax(-(mi_row * 4 + border - 8), -(((mi_row + mih) * 4) + 8));
+  S.lim.row_max = imin((P.mi_rows - mi_row - mih) * 4 + border - 8, (P.mi_rows - mi_row) * 4 + 8);
+  S.lim.col_min = imax(-(mi_col * 4 + border - 8), -(((mi_col + mih) * 4) + 8));
+  S.lim.col_max = imin((P.mi_cols - mi_col - mih) * 4 + border - 8, (P.mi_cols - mi_col) * 4 + 8);
+  S.lim.col_min = imax(S.lim.col_min, -1023);
+  S.lim.col_max = imin(S.lim.col_max, 1023);
+  S.lim.row_min = imax(S.lim.row_min, -1023);
+  S.lim.row_max = imin(S.lim.row_max, 1023);
+  const int off = it.y * P.pitch[0] + it.x;
+  S.src = src + off;
+  S.ref = ref + off;
+  const MV2 start = { (int)it.start_row, (int)it.start_col };
+  MV2 best;
+  full_pixel_search<T, W>(S, P, start, &best, smem_raw);
+  const int var = var_cost<T, W>(S, best.row, best.col);
+  if (lane == 0) {
+    results[blockIdx.x].row = (int16_t)best.row;
+    results[blockIdx.x].col = (int16_t)best.col;
+    results[blockIdx.x].var = var;
   }
 }
 

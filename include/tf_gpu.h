@@ -190,6 +190,30 @@ int tf_gpu_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, int row_begin, in
 int tf_gpu_output_device_plane(tf_gpu_ctx *ctx, int plane, void **dptr, size_t *pitch_bytes,
                                int *rows, int *row_bytes);
 
+/* First consumer beyond the temporal filter: the full-pixel search engine as a batch call.
+ * Every item is one block of `src` at luma position (x, y) searched in `ref` from a full-pel start MV with
+ * av1_full_pixel_search() (mcomp.c:1693-1832; NSTEP sites, cost_list == NULL) configured as tf_motion_search()
+ * configures it (temporal_filter.c:145-160: L1 MV cost class from the frame size, mesh search with the
+ * prune level / patterns of `params`, skip-row SAD with its audit): the search first_pass_motion_search()
+ * (firstpass.c:261-300) and TPL's motion_estimation() (tpl_model.c:285) run per 16x16 / 32x32 block with the
+ * same sites.  MV limits are those av1_set_mv_row_limits / av1_set_mv_col_limits (mcomp.h:216-240) give a
+ * block of that size at that position, clamped by av1_set_mv_search_range around a zero reference MV.
+ * block_size: 16 or 32; x must be a multiple of 16 and y of 4, the block inside the 8-aligned frame.
+ * Of `params` the fields bit_depth, mi_rows, mi_cols, cm_width/height, border_in_pixels, prune_mesh_level,
+ * mesh_patterns, use_downsampled_sad and q_factor are read.  results[i] = the best full-pel MV and
+ * get_mvpred_var_cost() at it, i.e. av1_full_pixel_search()'s return value. */
+typedef struct {
+  int x, y;                     /* luma position of the block's top-left sample */
+  int16_t start_row, start_col; /* full-pel start MV */
+} tf_gpu_search_item;
+typedef struct {
+  int16_t row, col; /* best full-pel MV */
+  int32_t var;      /* variance + MV cost at it (INT_MAX when the search was impossible) */
+} tf_gpu_search_result;
+int tf_gpu_fullpel_search_batch(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame *src,
+                                const tf_gpu_frame *ref, int block_size, const tf_gpu_search_item *items, int n,
+                                tf_gpu_search_result *results);
+
 /* Pinned host memory helpers so lookahead buffers can be DMA'd directly. */
 int tf_gpu_host_register(tf_gpu_ctx *ctx, void *ptr, size_t bytes);
 int tf_gpu_host_unregister(tf_gpu_ctx *ctx, void *ptr);

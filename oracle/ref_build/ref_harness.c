@@ -528,6 +528,84 @@ TFREF_API void tfref_run(void *h, int row_begin, int row_end, int16_t *mvs,
   tf_dealloc_data(&td->tf_data, c->use_hbd);
 }
 
+#pragma push_macro("buf")
+#undef buf /* struct buf_2d has a member of that name */
+/* av1_full_pixel_search() (mcomp.c:1693-1832) on one block, configured exactly as tf_motion_search()
+ * configures it (temporal_filter.c:104-160: NSTEP sites for the frame stride, step_param from the frame size,
+ * L1 MV cost class, mesh search on, LVL_1 pruning by q) -- the search first_pass_motion_search()
+ * (firstpass.c:261-300) and TPL's motion_estimation() (tpl_model.c:285) also run per block.  The block is the
+ * bsize x bsize (16 or 32) block of frame src_idx at luma position (x, y), searched in frame ref_idx from the
+ * full-pel start MV; MV limits from av1_set_mv_{row,col}_limits for that block.  out = {row, col, var}. */
+TFREF_API void tfref_full_pixel_search(void *h, int src_idx, int ref_idx, int bsize, int x, int y,
+                                       int start_row, int start_col, int *out) {
+  tfref_ctx *t = (tfref_ctx *)h;
+  AV1_COMP *cpi = t->cpi;
+  const tfref_cfg *c = &t->cfg;
+  tfref_setup_tf_ctx(t);
+  ThreadData *td = &cpi->td;
+  MACROBLOCK *mb = &td->mb;
+  MACROBLOCKD *mbd = &mb->e_mbd;
+  mbd->cur_buf = &t->frames[src_idx].entry.img;
+  mbd->bd = c->bit_depth;
+  for (int p = 0; p < 3; p++) {
+    mbd->plane[p].subsampling_x = p ? c->ss_x : 0;
+    mbd->plane[p].subsampling_y = p ? c->ss_y : 0;
+  }
+  mbd->error_info = &t->err;
+  tf_alloc_and_reset_data(&td->tf_data, t->num_pels, c->use_hbd);
+  tf_setup_macroblockd(mbd, &td->tf_data, &cpi->tf_ctx.sf);
+  const BLOCK_SIZE block_size = bsize == 32 ? BLOCK_32X32 : BLOCK_16X16;
+  const YV12_BUFFER_CONFIG *frame_to_filter = &t->frames[src_idx].entry.img;
+  const YV12_BUFFER_CONFIG *ref_frame = &t->frames[ref_idx].entry.img;
+  const int y_stride = frame_to_filter->y_stride;
+  const int y_offset = y * y_stride + x;
+  av1_set_mv_row_limits(&cpi->common.mi_params, &mb->mv_limits, y >> MI_SIZE_LOG2, bsize >> MI_SIZE_LOG2,
+                        cpi->oxcf.border_in_pixels);
+  av1_set_mv_col_limits(&cpi->common.mi_params, &mb->mv_limits, x >> MI_SIZE_LOG2, bsize >> MI_SIZE_LOG2,
+                        cpi->oxcf.border_in_pixels);
+  /* from here on: tf_motion_search() :94-160, verbatim in meaning */
+  const int min_frame_size = AOMMIN(cpi->common.width, cpi->common.height);
+  const struct buf_2d ori_src_buf = mb->plane[0].src;
+  const struct buf_2d ori_pre_buf = mbd->plane[0].pre[0];
+  FULLPEL_MOTION_SEARCH_PARAMS full_ms_params;
+  const SEARCH_METHODS search_method = NSTEP;
+  const search_site_config *search_site_cfg =
+      av1_get_search_site_config(mb->search_site_cfg_buf, &cpi->mv_search_params, search_method, y_stride);
+  const int step_param =
+      av1_init_search_range(AOMMAX(frame_to_filter->y_crop_width, frame_to_filter->y_crop_height));
+  const MV_COST_TYPE mv_cost_type =
+      min_frame_size >= 720 ? MV_COST_L1_HDRES
+                            : (min_frame_size >= 480 ? MV_COST_L1_MIDRES : MV_COST_L1_LOWRES);
+  FULLPEL_MV start_mv = { (int16_t)start_row, (int16_t)start_col };
+  const MV baseline_mv = kZeroMv;
+  mb->plane[0].src.buf = frame_to_filter->y_buffer + y_offset;
+  mb->plane[0].src.stride = y_stride;
+  mbd->plane[0].pre[0].buf = ref_frame->y_buffer + y_offset;
+  mbd->plane[0].pre[0].stride = y_stride;
+  int cost_list[5];
+  int_mv best_mv;
+  const int q = av1_get_q(cpi);
+  av1_make_default_fullpel_ms_params(&full_ms_params, cpi, mb, block_size, &baseline_mv, search_site_cfg,
+                                     /*fine_search_interval=*/0);
+  av1_set_mv_search_method(&full_ms_params, search_site_cfg, search_method);
+  full_ms_params.run_mesh_search = 1;
+  full_ms_params.mv_cost_params.mv_cost_type = mv_cost_type;
+  if (cpi->sf.mv_sf.prune_mesh_search == PRUNE_MESH_SEARCH_LVL_1) {
+    full_ms_params.prune_mesh_search = (q <= 20) ? 0 : 1;
+    full_ms_params.mesh_search_mv_diff_threshold = 2;
+  }
+  const int var = av1_full_pixel_search(start_mv, &full_ms_params, step_param, cond_cost_list(cpi, cost_list),
+                                        &best_mv.as_fullmv, NULL);
+  out[0] = best_mv.as_fullmv.row;
+  out[1] = best_mv.as_fullmv.col;
+  out[2] = var;
+  mb->plane[0].src = ori_src_buf;
+  mbd->plane[0].pre[0] = ori_pre_buf;
+  tf_dealloc_data(&td->tf_data, c->use_hbd);
+}
+
+#pragma pop_macro("buf")
+
 /* Output plane (full blocks region) as u16. w,h = number of samples copied. */
 TFREF_API void tfref_get_output(void *h, int plane, uint16_t *dst, int w, int hgt) {
   tfref_ctx *t = (tfref_ctx *)h;

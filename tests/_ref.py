@@ -91,6 +91,7 @@ def _bind(l):
     l.tfref_get_plane_with_border.restype = C.c_int
     l.tfref_get_plane_with_border.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
     l.tfref_extend_output_borders.argtypes = [C.c_void_p]
+    l.tfref_full_pixel_search.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.POINTER(C.c_int)]
     return l
 
 
@@ -210,6 +211,12 @@ class RefFilter:
 
     def extend_output_borders(self):
         self.L.tfref_extend_output_borders(self.h)
+
+    def full_pixel_search(self, src_idx, ref_idx, bsize, x, y, start_row, start_col):
+        """av1_full_pixel_search() on one block as tf_motion_search() configures it -> (row, col, var)."""
+        out = (C.c_int * 3)()
+        self.L.tfref_full_pixel_search(self.h, src_idx, ref_idx, bsize, x, y, start_row, start_col, out)
+        return out[0], out[1], out[2]
 
     def plane_with_border(self, idx, plane):
         ys, uvs, b, aw, ah = (C.c_int() for _ in range(5))
