@@ -767,6 +767,15 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
     ctx->s16_single_launch = m && strcmp(m, "single") == 0;
     const char *pr = getenv("TF_GPU_PRIO");
     if (pr && strcmp(pr, "flat") == 0) prio_hi = prio_lo;
+    // TF_GPU_CARVEOUT=<percent>: preferred shared-memory carveout of the search kernels (development switch)
+    const char *cv = getenv("TF_GPU_CARVEOUT");
+    if (cv && e == cudaSuccess) {
+      const int pct = atoi(cv);
+      cudaFuncSetAttribute(tf_search16_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(tf_search16_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(tf_search32_kernel<uint16_t, S32_WARPS_LO>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(tf_search32_kernel<uint8_t, S32_WARPS_LO>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_lo);

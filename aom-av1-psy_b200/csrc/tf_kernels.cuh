@@ -27,6 +27,28 @@
 namespace tfk {
 
 constexpr unsigned FULL = 0xffffffffu;
+// REDUX.SUM / REDUX.MIN warp reductions instead of shuffle trees: measured 52.25 vs 52.83 frames/s (4K 10-bit), off
+#ifndef TF_REDUX
+#define TF_REDUX 0
+#endif
+// Inlining policy of the search routines.  A routine that is not inlined into the kernel re-materialises the
+// global-memory descriptor for each of its loads (LDC + 2 x R2UR per LDG: 10% of the executed instructions
+// of both search kernels in the round-1 build) and passes its context through the stack.
+#ifndef TF_NI_SEARCH
+#define TF_NI_SEARCH __forceinline__
+#endif
+// Sub-pel / variance routines (many call sites): inlined for the 16x16 search (instruction-fetch stalls 12% -> 5%,
+// 548 -> 495 us per launch at 4K), out of line for the latency-bound 32x32 search whose inlined build fetches worse.
+#ifndef TF_INLINE_SUBPEL_W16
+#define TF_INLINE_SUBPEL_W16 1
+#endif
+#ifndef TF_INLINE_SUBPEL_W32
+#define TF_INLINE_SUBPEL_W32 0
+#endif
+template <int W>
+struct InlineSubpel {
+  static constexpr bool value = (W == 16) ? (TF_INLINE_SUBPEL_W16 != 0) : (TF_INLINE_SUBPEL_W32 != 0);
+};
 constexpr int MAXF = 24;
 constexpr int INT_MAX_ = 0x7fffffff;
 
@@ -89,7 +111,13 @@ struct Lim {
   int col_min, col_max, row_min, row_max;
 };
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int lane_id() {
+  // %laneid through non-volatile asm: the compiler may reuse one read per function instead of issuing an S2R
+  // at every inlined use (3% of the executed instructions of the 16x16 search)
+  int l;
+  asm("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
 __device__ __forceinline__ int iabs(int x) { return x < 0 ? -x : x; }
 __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
 __device__ __forceinline__ int imax(int a, int b) { return a > b ? a : b; }
@@ -111,10 +139,18 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // Warp sum of a per-lane (sum, sse) pair with one 64-bit reduction: |sum| <= 32 * 4095 < 2^17 per
 // lane, so sum + 2^17 is non-negative and the 32-lane total stays below 2^23; sse totals < 2^35.
 __device__ __forceinline__ unsigned long long warp_sum_pair(int &sum, unsigned sse) {
+#if TF_REDUX
+  // REDUX.SUM: one instruction per 32-bit warp sum (the result lands in a uniform register); the 32-bit
+  // per-lane sse is summed as two 16-bit halves so neither total can overflow
+  sum = __reduce_add_sync(FULL, sum);
+  const unsigned lo = __reduce_add_sync(FULL, sse & 0xffffu), hi = __reduce_add_sync(FULL, sse >> 16);
+  return ((unsigned long long)hi << 16) + lo;
+#else
   unsigned long long v = ((unsigned long long)sse << 24) | (unsigned)(sum + (1 << 17));
   v = warp_sum_u64(v);
   sum = (int)(v & 0xffffffu) - (1 << 22);
   return v >> 24;
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -174,7 +210,7 @@ struct WinCfg {
 
 // Cooperative, coalesced window fill: 16-byte global loads, 4-byte shared stores.
 template <typename T, int W>
-__device__ __noinline__ void window_load(Search<T> &S, unsigned char *buf, int wr, int wc) {
+__device__ TF_NI_SEARCH void window_load(Search<T> &S, unsigned char *buf, int wr, int wc) {
   using C = WinCfg<T, W>;
   const int lane = lane_id();
   const T *g0 = S.ref + (wr - C::R) * S.stride + (wc - C::R);
@@ -367,6 +403,9 @@ __device__ __forceinline__ unsigned reduce4_u32(const unsigned (&a)[4], int lane
 
 template <int FROM>
 __device__ __forceinline__ unsigned group_min_u32(unsigned v) {  // min across lane groups of FROM lanes
+#if TF_REDUX
+  return __reduce_min_sync(FULL, v);  // a group's lanes hold equal values: the warp minimum is the group minimum
+#endif
 #pragma unroll
   for (int o = FROM; o < 32; o <<= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
   return v;
@@ -446,8 +485,8 @@ __device__ __forceinline__ unsigned var_finish(int sum, unsigned long long sse, 
 }
 
 template <typename T, int W>
-__device__ __noinline__ unsigned variance(const T *a, int as, const T *b, int bs, int hbd_shift,
-                                          unsigned *sse_out) {
+__device__ __forceinline__ unsigned variance_body(const T *a, int as, const T *b, int bs, int hbd_shift,
+                                                  unsigned *sse_out) {
   const int lane = lane_id();
   constexpr int RP = 32 / W;  // rows per iteration
   const int col = lane % W, r0 = lane / W;
@@ -462,9 +501,18 @@ __device__ __noinline__ unsigned variance(const T *a, int as, const T *b, int bs
   const unsigned long long sse64 = warp_sum_pair(sum, sse);
   return var_finish(sum, sse64, W, hbd_shift, sse_out);
 }
+template <typename T, int W>
+__device__ __noinline__ unsigned variance_ni(const T *a, int as, const T *b, int bs, int hbd_shift, unsigned *sse_out) {
+  return variance_body<T, W>(a, as, b, bs, hbd_shift, sse_out);
+}
+template <typename T, int W>
+__device__ __forceinline__ unsigned variance(const T *a, int as, const T *b, int bs, int hbd_shift, unsigned *sse_out) {
+  if constexpr (InlineSubpel<W>::value) return variance_body<T, W>(a, as, b, bs, hbd_shift, sse_out);
+  else return variance_ni<T, W>(a, as, b, bs, hbd_shift, sse_out);
+}
 
 template <typename T, int W>
-__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int mode = 1);
+__device__ __forceinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int mode = 1);
 
 // get_mvpred_var_cost (mcomp.c:645-664): vf(src, ref@mv) + L1 cost.
 // For 16-bit samples the variance at a full-pel MV is the sub-pel error routine at phase (0, 0)
@@ -497,7 +545,7 @@ __device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
 // per-candidate code.
 // ---------------------------------------------------------------------------
 template <typename T, int W, bool SKIP>
-__device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start, int search_step, int *num00,
+__device__ TF_NI_SEARCH unsigned diamond_search(const Search<T> &S_in, MV2 start, int search_step, int *num00,
                                                 MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
   constexpr int PU = (W == 32) ? 2 : (L::MAXP < 3 ? L::MAXP : 3);  // passes whose loads are issued back to back
@@ -594,6 +642,14 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
           const int off = __shfl_sync(FULL, soff, i0 + u);
           part[u] = ((okmask >> (i0 + u)) & 1u) ? far_partial_off<T, W, SKIP>(far_base, off, S.stride, sf) : 0u;
         }
+#if TF_REDUX
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // every lane gets every total: no ownership, no final exchange
+          const unsigned tot = sad_post<SKIP>(__reduce_add_sync(FULL, part[u]), S.hbd_shift) + __shfl_sync(FULL, scost, i0 + u);
+          mykey = min(mykey, ((okmask >> (i0 + u)) & 1u) ? ((tot << 4) | (unsigned)(i0 + u + 1)) : 0xffffffffu);
+        }
+      }
+#else
         const unsigned tot4 = reduce4_u32(part, lane);
         const unsigned my_cost = __shfl_sync(FULL, scost, i0 + mine);
         const unsigned tot = sad_post<SKIP>(tot4, S.hbd_shift) + my_cost;
@@ -601,6 +657,7 @@ __device__ __noinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start
       }
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 8));
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 16));
+#endif
     }
     int best_site = 0;
     if ((mykey >> 4) < bestsad) {
@@ -682,7 +739,7 @@ __device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param,
 // group keeps the best key (total << 32 | visit index) of the candidates it
 // evaluated and one warp min-reduction at the end picks the winner.
 template <typename T, int W, bool SKIP>
-__device__ __noinline__ int mesh_search(const Search<T> &S_in, MV2 start, int range, int step, MV2 *best_out) {
+__device__ TF_NI_SEARCH int mesh_search(const Search<T> &S_in, MV2 start, int range, int step, MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
   constexpr int PU = 2;
   const Search<T> S = S_in;
@@ -783,7 +840,7 @@ __device__ int full_pixel_exhaustive(Search<T> &S, const KParams &P, MV2 start, 
 // Returns 1 when the skip-row result must be discarded and the search redone
 // with full SAD (mcomp.c:1777-1810).
 template <typename T, int W, bool SKIP>
-__device__ __noinline__ int full_pixel_search_pass(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv,
+__device__ TF_NI_SEARCH int full_pixel_search_pass(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv,
                                                    unsigned char *winbuf) {
   int run_mesh = 1;
   int var = full_pixel_diamond<T, W, SKIP>(S, start, P.step_param, best_mv);
@@ -854,7 +911,7 @@ __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2
 // mode 2: full-pel variance vf(ref, src); mode 3: full-pel variance vf(src, ref) (difference negated).
 // Modes 2 and 3 count as variance work in the instrumentation.
 template <typename T, int W>
-__device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int mode) {
+__device__ __forceinline__ unsigned bilinear_err_body(const Search<T> &S_in, int r8, int c8, int mode) {
   const Search<T> S = S_in;
   const int lane = lane_id();
   const int fr = r8 >> 3, fc = c8 >> 3;
@@ -932,6 +989,16 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
   return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
 }
 
+template <typename T, int W>
+__device__ __noinline__ unsigned bilinear_err_ni(const Search<T> &S, int r8, int c8, int mode) {
+  return bilinear_err_body<T, W>(S, r8, c8, mode);
+}
+template <typename T, int W>
+__device__ __forceinline__ unsigned bilinear_err(const Search<T> &S, int r8, int c8, int mode) {
+  if constexpr (InlineSubpel<W>::value) return bilinear_err_body<T, W>(S, r8, c8, mode);
+  else return bilinear_err_ni<T, W>(S, r8, c8, mode);
+}
+
 // The four first-level candidates of a sub-pel round (left, right, up, down of (tr, tc) at distance
 // hstep; first_level_check, mcomp.c:2503-2541) evaluated in one pass: their errors do not depend on the
 // incumbent, so the reference's sequential comparisons can be replayed on the four results afterwards.
@@ -940,7 +1007,7 @@ __device__ __noinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int
 // Candidates whose bit in validmask is clear are not read (their group re-reads the centre) and
 // return INT_MAX.  Same packed arithmetic as bilinear_err.
 template <typename T, int W>
-__device__ __noinline__ uint4 bilinear_err4(const Search<T> &S_in, int tr, int tc, int hstep, unsigned validmask) {
+__device__ __forceinline__ uint4 bilinear_err4_body(const Search<T> &S_in, int tr, int tc, int hstep, unsigned validmask) {
   const Search<T> S = S_in;
   constexpr int ES = (int)sizeof(T);
   constexpr int NP = W / 16;            // column pairs per lane
@@ -1033,6 +1100,16 @@ __device__ __noinline__ uint4 bilinear_err4(const Search<T> &S_in, int tr, int t
   out.z = __shfl_sync(FULL, mine, 16);
   out.w = __shfl_sync(FULL, mine, 24);
   return out;
+}
+
+template <typename T, int W>
+__device__ __noinline__ uint4 bilinear_err4_ni(const Search<T> &S, int tr, int tc, int hstep, unsigned validmask) {
+  return bilinear_err4_body<T, W>(S, tr, tc, hstep, validmask);
+}
+template <typename T, int W>
+__device__ __forceinline__ uint4 bilinear_err4(const Search<T> &S, int tr, int tc, int hstep, unsigned validmask) {
+  if constexpr (InlineSubpel<W>::value) return bilinear_err4_body<T, W>(S, tr, tc, hstep, validmask);
+  else return bilinear_err4_ni<T, W>(S, tr, tc, hstep, validmask);
 }
 
 __device__ __forceinline__ int clip_px(int v, int bd) {
@@ -1191,7 +1268,7 @@ __device__ void second_level_v2(Subpel<T, W> &sp, MV2 t, MV2 diag) {
 // av1_find_best_sub_pixel_tree{,_pruned,_pruned_more} (mcomp.c:2844-3133) with
 // cost_list == NULL, forced_stop = EIGHTH_PEL, MV_COST_NONE, unscaled refs.
 template <typename T, int W>
-__device__ __noinline__ unsigned subpel_search(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+__device__ __forceinline__ unsigned subpel_search_body(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
   Subpel<T, W> sp;
   sp.S = &S;
   sp.bd = P.is_hbd ? P.bit_depth : 8;
@@ -1235,6 +1312,16 @@ __device__ __noinline__ unsigned subpel_search(const Search<T> &S, const KParams
   return sp.besterr;
 }
 
+template <typename T, int W>
+__device__ __noinline__ unsigned subpel_search_ni(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+  return subpel_search_body<T, W>(S, P, start_full, best, tmp);
+}
+template <typename T, int W>
+__device__ __forceinline__ unsigned subpel_search(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+  if constexpr (InlineSubpel<W>::value) return subpel_search_body<T, W>(S, P, start_full, best, tmp);
+  else return subpel_search_ni<T, W>(S, P, start_full, best, tmp);
+}
+
 __device__ __forceinline__ int rawpel(int x) { return (x + 3 + (x >= 0)) >> 3; }  // GET_MV_RAWPEL mv.h:28
 
 // tf_motion_search (temporal_filter.c:87-253) is split along its own data
@@ -1272,7 +1359,10 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
 // 20 warps per SM) when the whole grid is resident at once (<= 148 * 20 blocks, e.g. 1080p), so
 // no second partial wave forms; MINB = 12 (168 registers, no spills) for larger grids, where the
 // latency-bound chain runs faster per launch and leaves registers for concurrent 16x16 launches.
-constexpr int S32_WARPS_HI = 20, S32_WARPS_LO = 12;
+#ifndef TF_S32_LO
+#define TF_S32_LO 12
+#endif
+constexpr int S32_WARPS_HI = 20, S32_WARPS_LO = TF_S32_LO;
 #ifndef TF_S16_WARPS
 #define TF_S16_WARPS 24
 #endif

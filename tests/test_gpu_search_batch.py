@@ -15,10 +15,10 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not _ref.available(), reason="
 
 CASES = [  # name, W, H, bit depth, clip motion, params
     ("cif8_s4", 352, 288, 8, (1, 2), {}),
-    ("cif10_s4", 352, 288, 10, (2, -3), {}),
+    ("cif10_s4", 352, 288, 10, (2, 3), {}),
     ("hd8_skip", 1280, 720, 8, (3, 5), {}),                  # >= 720p: skip-row SAD + audit, HDRES cost class
-    ("hd10_skip", 1280, 720, 10, (-4, 7), {}),
-    ("qcif8_s0_mesh", 176, 144, 8, (6, -9), dict(speed=0)),  # mesh search never pruned
+    ("hd10_skip", 1280, 720, 10, (4, 7), {}),
+    ("qcif8_s0_mesh", 176, 144, 8, (6, 9), dict(speed=0)),  # mesh search never pruned
     ("vga8_s3", 640, 480, 8, (0, 11), dict(speed=3, q_factor=12)),  # MIDRES cost class, LVL_1 pruning off (q <= 20)
     ("odd8", 200, 136, 8, (1, 1), {}),
 ]
