@@ -27,9 +27,11 @@
 namespace tfk {
 
 constexpr unsigned FULL = 0xffffffffu;
-// REDUX.SUM / REDUX.MIN warp reductions instead of shuffle trees: measured 52.25 vs 52.83 frames/s (4K 10-bit), off
-#ifndef TF_REDUX
-#define TF_REDUX 0
+// TF_FILT_WUNROLL: unroll factor of the weight loop of the filter kernel (0 = full, the co-located luma sums
+// of the chroma planes precomputed in registers).  Not unrolled: the filter kernel shrinks from 64 to 40 KB of
+// code (its instruction-cache request rate was 89% of peak) and loses its spills: 2.85 -> 2.65 ms at 4K 10-bit.
+#ifndef TF_FILT_WUNROLL
+#define TF_FILT_WUNROLL 1
 #endif
 // Inlining policy of the search routines.  A routine that is not inlined into the kernel re-materialises the
 // global-memory descriptor for each of its loads (LDC + 2 x R2UR per LDG: 10% of the executed instructions
@@ -139,18 +141,10 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // Warp sum of a per-lane (sum, sse) pair with one 64-bit reduction: |sum| <= 32 * 4095 < 2^17 per
 // lane, so sum + 2^17 is non-negative and the 32-lane total stays below 2^23; sse totals < 2^35.
 __device__ __forceinline__ unsigned long long warp_sum_pair(int &sum, unsigned sse) {
-#if TF_REDUX
-  // REDUX.SUM: one instruction per 32-bit warp sum (the result lands in a uniform register); the 32-bit
-  // per-lane sse is summed as two 16-bit halves so neither total can overflow
-  sum = __reduce_add_sync(FULL, sum);
-  const unsigned lo = __reduce_add_sync(FULL, sse & 0xffffu), hi = __reduce_add_sync(FULL, sse >> 16);
-  return ((unsigned long long)hi << 16) + lo;
-#else
   unsigned long long v = ((unsigned long long)sse << 24) | (unsigned)(sum + (1 << 17));
   v = warp_sum_u64(v);
   sum = (int)(v & 0xffffffu) - (1 << 22);
   return v >> 24;
-#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -403,9 +397,6 @@ __device__ __forceinline__ unsigned reduce4_u32(const unsigned (&a)[4], int lane
 
 template <int FROM>
 __device__ __forceinline__ unsigned group_min_u32(unsigned v) {  // min across lane groups of FROM lanes
-#if TF_REDUX
-  return __reduce_min_sync(FULL, v);  // a group's lanes hold equal values: the warp minimum is the group minimum
-#endif
 #pragma unroll
   for (int o = FROM; o < 32; o <<= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
   return v;
@@ -642,14 +633,6 @@ __device__ TF_NI_SEARCH unsigned diamond_search(const Search<T> &S_in, MV2 start
           const int off = __shfl_sync(FULL, soff, i0 + u);
           part[u] = ((okmask >> (i0 + u)) & 1u) ? far_partial_off<T, W, SKIP>(far_base, off, S.stride, sf) : 0u;
         }
-#if TF_REDUX
-#pragma unroll
-        for (int u = 0; u < 4; u++) {  // every lane gets every total: no ownership, no final exchange
-          const unsigned tot = sad_post<SKIP>(__reduce_add_sync(FULL, part[u]), S.hbd_shift) + __shfl_sync(FULL, scost, i0 + u);
-          mykey = min(mykey, ((okmask >> (i0 + u)) & 1u) ? ((tot << 4) | (unsigned)(i0 + u + 1)) : 0xffffffffu);
-        }
-      }
-#else
         const unsigned tot4 = reduce4_u32(part, lane);
         const unsigned my_cost = __shfl_sync(FULL, scost, i0 + mine);
         const unsigned tot = sad_post<SKIP>(tot4, S.hbd_shift) + my_cost;
@@ -657,7 +640,9 @@ __device__ TF_NI_SEARCH unsigned diamond_search(const Search<T> &S_in, MV2 start
       }
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 8));
       mykey = min(mykey, __shfl_xor_sync(FULL, mykey, 16));
-#endif
+      // (Measured and rejected in round 2, same box A/B at 4K 10-bit: REDUX.SUM / REDUX.MIN instead of the shuffle
+      // trees 52.25 vs 52.83 frames/s; an L1 prefetch (CCTL.PF1) of every live candidate of the stage before the
+      // loop 53.9 vs 56.3; live candidates packed four to a pass instead of fixed groups 55.8 vs 56.3.)
     }
     int best_site = 0;
     if ((mykey >> 4) < bestsad) {
@@ -1362,7 +1347,13 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
 #ifndef TF_S32_LO
 #define TF_S32_LO 12
 #endif
-constexpr int S32_WARPS_HI = 20, S32_WARPS_LO = TF_S32_LO;
+#ifndef TF_S32_HI
+#define TF_S32_HI 20
+#endif
+#ifndef TF_S32_HI_HBD
+#define TF_S32_HI_HBD 16
+#endif
+constexpr int S32_WARPS_HI = TF_S32_HI, S32_WARPS_HI_HBD = TF_S32_HI_HBD, S32_WARPS_LO = TF_S32_LO;
 #ifndef TF_S16_WARPS
 #define TF_S16_WARPS 24
 #endif
@@ -1747,17 +1738,21 @@ __device__ __forceinline__ int tf_weight(double scaled_error) {
 }
 
 template <typename T>
-__device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row, int mb_col, const MV2 *mvs,
+__device__ void apply_filter(const KParams &P, const T *curb, int mb_row, int mb_col, const MV2 *mvs,
                              const int *mses, const T *pred, uint32_t *accum, uint16_t *count, uint32_t *sq,
                              uint32_t *lsum, const double *terms /* shared: d_factor[4], block_error * inv_factor [4] */) {
   constexpr int NT = FILT_THREADS;
   constexpr int MAXPX = 1024 / NT;  // pixels of one plane per thread
+  constexpr int WUNROLL = TF_FILT_WUNROLL > 0 ? TF_FILT_WUNROLL : 1;
+  (void)WUNROLL;
   const int tid = threadIdx.x, lane = tid & 31;
   const double inv_factor = 1.0 / ((5 + 1) * 20);
   const double weight_factor = (double)5 * inv_factor;
   (void)mvs;
   (void)mses;
   (void)inv_factor;
+  (void)mb_row;
+  (void)mb_col;
   uint32_t lsub[MAXPX];  // chroma: sums of the co-located luma squares of this thread's pixels
   int plane_offset = 0;
   for (int plane = 0; plane < P.num_planes; plane++) {
@@ -1766,15 +1761,13 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
     const int rpp = NT >> wsh;    // rows per pass over the plane
     const int npass = n / NT;     // 8 (32x32), 4 (16x32), 2 (16x16)
     const int j = tid & (w - 1), r0 = tid >> wsh;
-    const int st = P.pitch[plane > 0];
-    const T *src = cur[plane] + mb_row * h * st + mb_col * w;
     const int num_ref_pixels = 25 + (plane ? (1 << (ssx + ssy)) : 0);
     const double inv_num_ref_pixels = 1.0 / num_ref_pixels;
     // lanes holding the horizontal neighbours of this pixel's row, edge-clamped
     const int seg = lane & ~(w - 1);
     const int l_m2 = seg + imax(j - 2, 0), l_m1 = seg + imax(j - 1, 0);
     const int l_p1 = seg + imin(j + 1, w - 1), l_p2 = seg + imin(j + 2, w - 1);
-    if (plane == 1) {  // compute_luma_sq_error_sum (:507-522); lsum holds the raw luma squares
+    if (TF_FILT_WUNROLL == 0 && plane == 1) {  // compute_luma_sq_error_sum (:507-522); lsum holds the raw luma squares
 #pragma unroll
       for (int k = 0; k < MAXPX; k++) {
         if (k < npass) {
@@ -1790,8 +1783,8 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
 #pragma unroll
     for (int k = 0; k < MAXPX; k++) {
       if (k < npass) {
-        const int i = r0 + k * rpp, idx = tid + k * NT;  // == i * w + j
-        const int d = (int)__ldg(src + i * st + j) - (int)pred[plane_offset + idx];
+        const int idx = tid + k * NT;  // == (r0 + k * rpp) * w + j
+        const int d = (int)curb[plane_offset + idx] - (int)pred[plane_offset + idx];
         const uint32_t v = (uint32_t)(d * d);
         if (plane == 0 && P.num_planes > 1) lsum[idx] = v;
         const uint32_t h5 = v + __shfl_sync(FULL, v, l_m2) + __shfl_sync(FULL, v, l_m1) + __shfl_sync(FULL, v, l_p1) +
@@ -1805,14 +1798,25 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
     // a thread's pixels lie in one column half, i.e. in two sub-blocks: the upper and the lower one
     const double d_factor[2] = { terms[sb_col], terms[2 + sb_col] };
     const double b_term[2] = { terms[4 + sb_col], terms[6 + sb_col] };
+#if TF_FILT_WUNROLL == 0
 #pragma unroll
+#else
+#pragma unroll(WUNROLL)
+#endif
     for (int k = 0; k < MAXPX; k++) {
       if (k < npass) {
         const int i = r0 + k * rpp, idx = tid + k * NT;
         // 25 (+4) squares of at most 4095^2: fits 32 bits
         uint32_t sum_square_diff = sq[imax(i - 2, 0) * w + j] + sq[imax(i - 1, 0) * w + j] + sq[idx] +
                                    sq[imin(i + 1, h - 1) * w + j] + sq[imin(i + 2, h - 1) * w + j];
+#if TF_FILT_WUNROLL == 0
         if (plane) sum_square_diff += lsub[k];
+#else
+        if (plane) {  // compute_luma_sq_error_sum (:507-522) on the fly: the loop is not fully unrolled
+          for (int ii = 0; ii < (1 << ssy); ii++)
+            for (int jj = 0; jj < (1 << ssx); jj++) sum_square_diff += lsum[((i << ssy) + ii) * 32 + (j << ssx) + jj];
+        }
+#endif
         sum_square_diff >>= hbd_sh;
         const double window_error = __dmul_rn((double)sum_square_diff, inv_num_ref_pixels);
         const int sb = (i >= h / 2);  // rows ascend with k: the first half of the passes is the upper sub-block
@@ -1838,18 +1842,18 @@ __device__ void apply_filter(const KParams &P, const T *const cur[3], int mb_row
 // Block-private shared memory, carved at run time (num_pels = 1024 luma + chroma:
 // 1536 for 4:2:0, 2048 for 4:2:2, 3072 for 4:4:4):
 //   accum u32[num_pels] | sq u32[1024] | lsum u32[1024] | count u16[num_pels] |
-//   pred (T view of u16[num_pels]) | im i16[FILT_WARPS][27*16] | red u64[FILT_WARPS]
+//   pred (T view of u16[num_pels]) | cur (T view of u16[num_pels]) | im i16[FILT_WARPS][27*16] | red u64[FILT_WARPS]
 // ---------------------------------------------------------------------------
 struct WarpSmem {
   double *terms;  // per frame: d_factor of the four sub-blocks, then block_error * inv_factor
   uint32_t *accum, *sq, *lsum;
-  uint16_t *count, *pred;
+  uint16_t *count, *pred, *cur;  // cur: the block of the frame to filter, in pred's layout (read once per block)
   int16_t *im;
   unsigned long long *red;
 };
 constexpr int FILT_IM = (16 + 12) * 16;  // intermediate of one 2-D 12-tap sub-block (transposed form: 16 columns of pitch 28)
 __host__ __device__ inline size_t filter_smem_bytes(int num_pels) {
-  return (size_t)num_pels * 8 + 2 * 1024 * 4 + FILT_WARPS * FILT_IM * 2 + FILT_WARPS * 8 + 8 * 8;
+  return (size_t)num_pels * 10 + 2 * 1024 * 4 + FILT_WARPS * FILT_IM * 2 + FILT_WARPS * 8 + 8 * 8;
 }
 __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels) {
   WarpSmem sm;
@@ -1860,7 +1864,8 @@ __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels)
   sm.lsum = sm.sq + 1024;
   sm.count = reinterpret_cast<uint16_t *>(sm.lsum + 1024);
   sm.pred = sm.count + num_pels;
-  sm.im = reinterpret_cast<int16_t *>(sm.pred + num_pels);
+  sm.cur = sm.pred + num_pels;
+  sm.im = reinterpret_cast<int16_t *>(sm.cur + num_pels);
   return sm;
 }
 
@@ -1879,10 +1884,21 @@ __global__ void __launch_bounds__(FILT_THREADS, TF_FILT_MINB) tf_filter_kernel(c
     sm.accum[i] = 0;
     sm.count[i] = 0;
   }
-  __syncthreads();
-
   const T *cur[3];
   for (int pl = 0; pl < 3; pl++) cur[pl] = reinterpret_cast<const T *>(P.frm[P.filter_idx][pl]);
+  // the block of the frame to filter is compared with the predictor of every frame: one global read
+  T *curb = reinterpret_cast<T *>(sm.cur);
+  {
+    int off = 0;
+    for (int pl = 0; pl < P.num_planes; pl++) {
+      const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.pitch[pl > 0];
+      const int wsh = 5 - (pl ? P.ss_x : 0);
+      const T *b = cur[pl] + mb_row * h * st + mb_col * w;
+      for (int idx = tid; idx < h * w; idx += NT) curb[off + idx] = __ldg(b + (idx >> wsh) * st + (idx & (w - 1)));
+      off += h * w;
+    }
+  }
+  __syncthreads();
 
   for (int frame = 0; frame < P.num_frames; frame++) {
     if (frame == P.filter_idx) {
@@ -1891,10 +1907,10 @@ __global__ void __launch_bounds__(FILT_THREADS, TF_FILT_MINB) tf_filter_kernel(c
       for (int pl = 0; pl < P.num_planes; pl++) {
         const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.pitch[pl > 0];
         const int wsh = 5 - (pl ? P.ss_x : 0);
-        const T *b = cur[pl] + mb_row * h * st + mb_col * w;
+        (void)st;
+        (void)wsh;
         for (int idx = tid; idx < h * w; idx += NT) {
-          const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
-          sm.accum[off + idx] += 1000u * (uint32_t)__ldg(b + i * st + j);
+          sm.accum[off + idx] += 1000u * (uint32_t)curb[off + idx];
           sm.count[off + idx] = (uint16_t)(sm.count[off + idx] + 1000);
         }
         off += h * w;
@@ -1958,7 +1974,7 @@ __global__ void __launch_bounds__(FILT_THREADS, TF_FILT_MINB) tf_filter_kernel(c
     }
     if (P.d_pred)
       for (int i = tid; i < P.num_pels; i += NT) P.d_pred[bf * P.num_pels + i] = (uint16_t)pred[i];
-    apply_filter<T>(P, cur, mb_row, mb_col, sub_mvs, sub_mses, pred, sm.accum, sm.count, sm.sq, sm.lsum, sm.terms);
+    apply_filter<T>(P, curb, mb_row, mb_col, sub_mvs, sub_mses, pred, sm.accum, sm.count, sm.sq, sm.lsum, sm.terms);
   }
 
   // tf_normalize_filtered_frame (:740-777); OD_DIVU == integer division here
@@ -1971,14 +1987,13 @@ __global__ void __launch_bounds__(FILT_THREADS, TF_FILT_MINB) tf_filter_kernel(c
       const int h = 32 >> (pl ? P.ss_y : 0), w = 32 >> (pl ? P.ss_x : 0), st = P.out_pitch[pl > 0];
       const int wsh = 5 - (pl ? P.ss_x : 0);
       T *o = reinterpret_cast<T *>(P.out[pl]) + mb_row * h * st + mb_col * w;
-      const T *a = cur[pl] + mb_row * h * P.pitch[pl > 0] + mb_col * w;
       for (int idx = tid; idx < h * w; idx += NT) {
         const int i = idx >> wsh, j = idx & (w - 1);  // w is 32 or 16
         const uint32_t c = sm.count[off + idx];
         const uint32_t v = (sm.accum[off + idx] + (c >> 1)) / c;
         o[i * st + j] = (T)v;
         if (pl == 0 && P.compute_diff) {
-          const int d = (int)__ldg(a + i * P.pitch[0] + j) - (int)v;
+          const int d = (int)curb[off + idx] - (int)v;
           sse += (unsigned)(d * d);
         }
       }
