@@ -501,7 +501,6 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   }
   const int grid = (K.row_end - K.row_begin) * K.mb_cols;
   if (grid <= 0) return fail(ctx, TF_GPU_ERR_INVALID, "empty row range");
-  const size_t smem_search = WIN_BYTES;
   const size_t smem_filter = filter_smem_bytes(K.num_pels);
   const int nref = p->num_frames - 1;
   // the frame to filter is read by every kernel
@@ -526,11 +525,11 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
       const int hi = g.is_hbd ? S32_WARPS_HI_HBD : S32_WARPS_HI;
       const bool one_wave = grid <= ctx->num_sms * hi && grid > ctx->num_sms * S32_WARPS_LO;
       if (g.is_hbd) {
-        if (one_wave) tf_search32_kernel<uint16_t, S32_WARPS_HI_HBD><<<grid, 32, smem_search, ctx->stream>>>(Kf);
-        else tf_search32_kernel<uint16_t, S32_WARPS_LO><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+        if (one_wave) tf_search32_kernel<uint16_t, S32_WARPS_HI_HBD><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
+        else tf_search32_kernel<uint16_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
       } else {
-        if (one_wave) tf_search32_kernel<uint8_t, S32_WARPS_HI><<<grid, 32, smem_search, ctx->stream>>>(Kf);
-        else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, smem_search, ctx->stream>>>(Kf);
+        if (one_wave) tf_search32_kernel<uint8_t, S32_WARPS_HI><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
+        else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
       }
       nlaunch++;
       if (!p->force_integer_mv && !ctx->s16_single_launch) {
@@ -541,8 +540,8 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
         KParams K16 = Kf;
         // task decode expects [frame_begin, frame_end) minus the centre: a single non-centre frame
         K16.filter_idx = K.filter_idx;
-        if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4, 32, WIN16_BYTES, ctx->stream2>>>(K16);
-        else tf_search16_kernel<uint8_t><<<grid * 4, 32, WIN16_BYTES, ctx->stream2>>>(K16);
+        if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4, 32, SearchSmem<uint16_t, 16>::TOTAL, ctx->stream2>>>(K16);
+        else tf_search16_kernel<uint8_t><<<grid * 4, 32, SearchSmem<uint8_t, 16>::TOTAL, ctx->stream2>>>(K16);
         nlaunch++;
         any16 = true;
       }
@@ -552,8 +551,8 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
       KParams K16 = K;
       K16.frame_begin = 0;
       K16.frame_end = p->num_frames;
-      if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4 * nref, 32, WIN16_BYTES, ctx->stream>>>(K16);
-      else tf_search16_kernel<uint8_t><<<grid * 4 * nref, 32, WIN16_BYTES, ctx->stream>>>(K16);
+      if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4 * nref, 32, SearchSmem<uint16_t, 16>::TOTAL, ctx->stream>>>(K16);
+      else tf_search16_kernel<uint8_t><<<grid * 4 * nref, 32, SearchSmem<uint8_t, 16>::TOTAL, ctx->stream>>>(K16);
       nlaunch++;
     }
     if (any16) {

@@ -27,6 +27,11 @@
 namespace tfk {
 
 constexpr unsigned FULL = 0xffffffffu;
+// TF_S32_ERR4: the 32x32 search evaluates the four first-level sub-pel candidates in one batched pass like the
+// 16x16 search (fewer instructions, longer dependent chain per warp).
+#ifndef TF_S32_ERR4
+#define TF_S32_ERR4 1
+#endif
 // TF_FILT_WUNROLL: unroll factor of the weight loop of the filter kernel (0 = full, the co-located luma sums
 // of the chroma planes precomputed in registers).  Not unrolled: the filter kernel shrinks from 64 to 40 KB of
 // code (its instruction-cache request rate was 89% of peak) and loses its spills: 2.85 -> 2.65 ms at 4K 10-bit.
@@ -39,13 +44,14 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef TF_NI_SEARCH
 #define TF_NI_SEARCH __forceinline__
 #endif
-// Sub-pel / variance routines (many call sites): inlined for the 16x16 search (instruction-fetch stalls 12% -> 5%,
-// 548 -> 495 us per launch at 4K), out of line for the latency-bound 32x32 search whose inlined build fetches worse.
+// Sub-pel / variance routines (many call sites): inlined as well (16x16 search: instruction-fetch stalls 12% -> 5%,
+// 548 -> 495 us per launch at 4K).  For the 32x32 search inlining only pays together with the batched first-level
+// pass (TF_S32_ERR4: four out-of-line calls become one inlined pass): 60.4 -> 61.5 frames/s at 4K 10-bit.
 #ifndef TF_INLINE_SUBPEL_W16
 #define TF_INLINE_SUBPEL_W16 1
 #endif
 #ifndef TF_INLINE_SUBPEL_W32
-#define TF_INLINE_SUBPEL_W32 0
+#define TF_INLINE_SUBPEL_W32 1
 #endif
 template <int W>
 struct InlineSubpel {
@@ -164,6 +170,7 @@ struct Search {
   // are read from shared memory (one conflict-free wavefront per load), the rest
   // from global memory through L1.
   unsigned char *win;  // nullptr = no window
+  unsigned srcs;       // shared address of the source-block tile (SrcTile layout), 0 = not staged
   int wr, wc, wR;
   int wpitch;  // bytes; wpitch/4 is odd
   int wshift;  // bytes the window origin was aligned down by
@@ -201,6 +208,42 @@ struct WinCfg {
   static constexpr int PITCH = ROWB + 4 + ((((ROWB + 4) / 4) & 1) ? 0 : 4);         // words per row odd
   static_assert(ROWS * PITCH <= (W == 32 ? WIN_BYTES : WIN16_BYTES), "search window does not fit");
 };
+
+// The block of the frame to filter as a shared-memory tile for the sub-pel stage: W rows, row pitch chosen so
+// that the row bands of the error routines below fall into disjoint banks.
+template <typename T, int W>
+struct SrcTile {
+  static constexpr int PITCH = sizeof(T) == 2 ? (W == 32 ? 68 : 40) : (W == 32 ? 36 : 20);  // bytes
+  static constexpr int BYTES = W * PITCH;
+};
+// Dynamic shared memory of a search kernel: the window, then the source tile.
+template <typename T, int W>
+struct SearchSmem {
+  static constexpr int WIN = (WinCfg<T, W>::ROWS * WinCfg<T, W>::PITCH + 15) / 16 * 16;
+  static constexpr int TOTAL = WIN + SrcTile<T, W>::BYTES;
+  static_assert((W + 7) * W * (int)sizeof(T) <= WIN, "8-tap scratch of SUBPEL_TREE lives in the window buffer");
+};
+template <typename T, int W>
+__device__ __forceinline__ void src_tile_load(Search<T> &S, unsigned char *buf) {
+  constexpr int ES = (int)sizeof(T), CPR = W * ES / 16, TOTAL = W * CPR;  // 16-byte chunks
+  const int lane = lane_id();
+  const unsigned char *g = reinterpret_cast<const unsigned char *>(S.src);
+  const size_t gpitch = (size_t)S.stride * ES;
+#pragma unroll
+  for (int q0 = 0; q0 < TOTAL; q0 += 32) {
+    const int q = q0 + lane, row = q / CPR, ch = q - row * CPR;
+    if (q < TOTAL) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(g + row * gpitch) + ch);
+      uint32_t *d = reinterpret_cast<uint32_t *>(buf + row * SrcTile<T, W>::PITCH + ch * 16);
+      d[0] = v.x;
+      d[1] = v.y;
+      d[2] = v.z;
+      d[3] = v.w;
+    }
+  }
+  __syncwarp();
+  S.srcs = (unsigned)__cvta_generic_to_shared(buf);
+}
 
 // Cooperative, coalesced window fill: 16-byte global loads, 4-byte shared stores.
 template <typename T, int W>
@@ -319,6 +362,11 @@ __device__ __forceinline__ unsigned sad_partial(const SadSrc &Q, const unsigned 
 __device__ __forceinline__ uint32_t lds_u32(unsigned addr) {
   uint32_t v;
   asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(unsigned addr) {
+  uint32_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 template <typename T, int W, bool SKIP>
@@ -1097,6 +1145,194 @@ __device__ __forceinline__ uint4 bilinear_err4(const Search<T> &S, int tr, int t
   else return bilinear_err4_ni<T, W>(S, tr, tc, hstep, validmask);
 }
 
+// ---------------------------------------------------------------------------
+// Sub-pel error out of shared memory only.  subpel_search() makes sure the search window covers every
+// candidate of the sub-pel stage (all lie within two full-pel steps of its start) and the source block is
+// staged as a tile, so these routines use ld.shared with 32-bit addresses and compile-time row pitches (no
+// generic loads, no 64-bit address arithmetic per row).  Same taps and rounding as bilinear_err; the error
+// terms use a biased difference: d' = v + 4096 - s is positive in both halves of the register, so one IADD3
+// replaces max / min / subtract, one IDP.2A sums it, and
+//   sum(d) = sum(d') - 4096 n,   sum(d^2) = sum(d'^2) - 8192 sum(d') + n 2^24   (exact; evaluated mod 2^32,
+// the true per-lane value is below 2^32).
+// ---------------------------------------------------------------------------
+#ifndef TF_SUBPEL_WIN
+#define TF_SUBPEL_WIN 1
+#endif
+template <typename T, int W>
+__device__ __forceinline__ unsigned win_origin(const Search<T> &S) {  // shared address of MV (0, 0), row 0
+  return (unsigned)__cvta_generic_to_shared(S.win) +
+         (unsigned)((S.wR - S.wr) * WinCfg<T, W>::PITCH + (S.wR - S.wc) * (int)sizeof(T) + S.wshift);
+}
+template <typename T, int W>
+__device__ __forceinline__ unsigned subpel_err_win_body(const Search<T> &S_in, int r8, int c8, int mode) {
+  const Search<T> S = S_in;
+  const int lane = lane_id();
+  const int fr = r8 >> 3, fc = c8 >> 3;
+  const int xo = c8 & 7, yo = r8 & 7;
+  constexpr int ES = (int)sizeof(T);
+  constexpr int WP = WinCfg<T, W>::PITCH, SP = SrcTile<T, W>::PITCH;
+  constexpr int PAIRS = W / 2, BANDS = 32 / PAIRS, BROWS = W / BANDS;
+  constexpr int CH = BROWS < 8 ? BROWS : 8;
+  const int j = lane % PAIRS, rbeg = (lane / PAIRS) * BROWS;
+  const unsigned a = win_origin<T, W>(S) + (unsigned)((fr + rbeg) * WP + (fc + 2 * j) * ES);
+  const unsigned wa = a & ~3u, sh = (a & 3u) * 8;
+  const unsigned sa = S.srcs + (unsigned)(rbeg * SP + 2 * j * ES);
+  const unsigned m0 = 8 - xo, m1 = xo, n0 = 8 - yo, n1 = yo;
+  constexpr unsigned RND = 0x00040004u, MSK = 0x1fff1fffu, BIAS = 0x10001000u;
+  auto hrow = [&](uint32_t w0, uint32_t w1) -> unsigned {
+    unsigned A, B;
+    if (ES == 2) {
+      A = __funnelshift_rc(w0, w1, sh);
+      B = __funnelshift_rc(w0, w1, sh + 16);
+    } else {
+      const unsigned x = __funnelshift_r(w0, w1, sh);
+      A = __byte_perm(x, 0, 0x4140);
+      B = __byte_perm(x, 0, 0x4241);
+    }
+    return ((A * m0 + (B * m1 + RND)) >> 3) & MSK;
+  };
+  unsigned hprev = hrow(lds_u32(wa), lds_u32(wa + 4));
+  unsigned accs = 0, accl = 0, acch = 0;
+#pragma unroll 1
+  for (int t0 = 0; t0 < BROWS; t0 += CH) {
+    uint32_t w0[CH], w1[CH], sv[CH];
+    const unsigned wb = wa + (unsigned)((t0 + 1) * WP), sb = sa + (unsigned)(t0 * SP);
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      w0[k] = lds_u32(wb + k * WP);
+      w1[k] = lds_u32(wb + k * WP + 4);
+    }
+#pragma unroll
+    for (int k = 0; k < CH; k++) sv[k] = ES == 2 ? lds_u32(sb + k * SP) : __byte_perm(lds_u16(sb + k * SP), 0, 0x4140);
+#pragma unroll
+    for (int k = 0; k < CH; k++) {
+      const unsigned hn = hrow(w0[k], w1[k]);
+      const unsigned v = ((hprev * n0 + (hn * n1 + RND)) >> 3) & MSK;
+      hprev = hn;
+      const unsigned dp = v + BIAS - sv[k];
+      const unsigned pb = __byte_perm(dp, 0, 0x3120);
+      accs = __dp2a_lo(dp, 0x0101u, accs);
+      accl = __dp2a_lo(dp, pb, accl);
+      acch = __dp2a_hi(dp, pb, acch);
+    }
+  }
+  if (S.ctr && lane == 0) atomicAdd(&S.ctr[mode == 1 ? 1 : 2], (unsigned long long)(W * W));
+  constexpr int NL = BROWS * 2;  // samples per lane
+  const int sumd = (int)accs - NL * 4096;
+  const unsigned sse = accl + (acch << 8) - (accs << 13) + (unsigned)NL * (1u << 24);
+  int sum = mode == 3 ? -sumd : sumd;
+  const unsigned long long sse64 = warp_sum_pair(sum, sse);
+  unsigned sse_out;
+  return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
+}
+template <typename T, int W>
+__device__ __noinline__ unsigned subpel_err_win_ni(const Search<T> &S, int r8, int c8, int mode) {
+  return subpel_err_win_body<T, W>(S, r8, c8, mode);
+}
+template <typename T, int W>
+__device__ __forceinline__ unsigned subpel_err_win(const Search<T> &S, int r8, int c8, int mode) {
+  if constexpr (InlineSubpel<W>::value) return subpel_err_win_body<T, W>(S, r8, c8, mode);
+  else return subpel_err_win_ni<T, W>(S, r8, c8, mode);
+}
+
+// The batched first-level pass (see bilinear_err4) out of shared memory only.
+template <typename T, int W>
+__device__ __forceinline__ uint4 subpel_err4_win_body(const Search<T> &S_in, int tr, int tc, int hstep, unsigned validmask) {
+  const Search<T> S = S_in;
+  constexpr int ES = (int)sizeof(T);
+  constexpr int WP = WinCfg<T, W>::PITCH, SP = SrcTile<T, W>::PITCH;
+  constexpr int NP = W / 16;
+  constexpr int CH = NP == 1 ? 8 : 4;
+  const int lane = lane_id(), g = lane >> 3, u = lane & 7;
+  const bool valid = (validmask >> g) & 1u;
+  int r8 = tr, c8 = tc;
+  if (valid) {
+    if (g == 0) c8 -= hstep;
+    else if (g == 1) c8 += hstep;
+    else if (g == 2) r8 -= hstep;
+    else r8 += hstep;
+  }
+  const int fr = r8 >> 3, fc = c8 >> 3;
+  const unsigned xo = c8 & 7, yo = r8 & 7;
+  const unsigned a = win_origin<T, W>(S) + (unsigned)(fr * WP + (fc + 2 * u) * ES);
+  const unsigned wa = a & ~3u, sh = (a & 3u) * 8;  // 16 pairs further on is a multiple of 4 bytes: same shift
+  const unsigned sa = S.srcs + (unsigned)(2 * u * ES);
+  const unsigned m0 = 8 - xo, m1 = xo, n0 = 8 - yo, n1 = yo;
+  constexpr unsigned RND = 0x00040004u, MSK = 0x1fff1fffu, BIAS = 0x10001000u;
+  auto hrow = [&](uint32_t w0, uint32_t w1) -> unsigned {
+    unsigned A, B;
+    if (ES == 2) {
+      A = __funnelshift_rc(w0, w1, sh);
+      B = __funnelshift_rc(w0, w1, sh + 16);
+    } else {
+      const unsigned x = __funnelshift_r(w0, w1, sh);
+      A = __byte_perm(x, 0, 0x4140);
+      B = __byte_perm(x, 0, 0x4241);
+    }
+    return ((A * m0 + (B * m1 + RND)) >> 3) & MSK;
+  };
+  unsigned hprev[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) hprev[p] = hrow(lds_u32(wa + p * 16 * ES), lds_u32(wa + p * 16 * ES + 4));
+  unsigned accs = 0, accl = 0, acch = 0;
+#pragma unroll 1
+  for (int t0 = 0; t0 < W; t0 += CH) {
+    uint32_t w0[CH][NP], w1[CH][NP], sv[CH][NP];
+    const unsigned wb = wa + (unsigned)((t0 + 1) * WP), sb = sa + (unsigned)(t0 * SP);
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        w0[k][p] = lds_u32(wb + k * WP + p * 16 * ES);
+        w1[k][p] = lds_u32(wb + k * WP + p * 16 * ES + 4);
+      }
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+#pragma unroll
+      for (int p = 0; p < NP; p++)
+        sv[k][p] = ES == 2 ? lds_u32(sb + k * SP + p * 16 * ES) : __byte_perm(lds_u16(sb + k * SP + p * 16 * ES), 0, 0x4140);
+#pragma unroll
+    for (int k = 0; k < CH; k++)
+#pragma unroll
+      for (int p = 0; p < NP; p++) {
+        const unsigned hn = hrow(w0[k][p], w1[k][p]);
+        const unsigned v = ((hprev[p] * n0 + (hn * n1 + RND)) >> 3) & MSK;
+        hprev[p] = hn;
+        const unsigned dp = v + BIAS - sv[k][p];
+        const unsigned pb = __byte_perm(dp, 0, 0x3120);
+        accs = __dp2a_lo(dp, 0x0101u, accs);
+        accl = __dp2a_lo(dp, pb, accl);
+        acch = __dp2a_hi(dp, pb, acch);
+      }
+  }
+  if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(__popc(validmask & 15u) * W * W));
+  constexpr int NL = W * NP * 2;  // samples per lane
+  const int sumd = (int)accs - NL * 4096;
+  const unsigned sse = accl + (acch << 8) - (accs << 13) + (unsigned)NL * (1u << 24);
+  // (sum, sse) of a candidate = totals over its 8 lanes: |sum| < 2^19 per lane, sse totals < 2^35
+  unsigned long long pk = ((unsigned long long)sse << 24) | (unsigned)(sumd + (1 << 19));
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) pk += __shfl_xor_sync(FULL, pk, o);
+  const int sum = (int)(pk & 0xffffffu) - (1 << 22);
+  unsigned sse_out;
+  const unsigned mine = valid ? var_finish(sum, pk >> 24, W, S.hbd_shift, &sse_out) : (unsigned)INT_MAX_;
+  uint4 out;
+  out.x = __shfl_sync(FULL, mine, 0);
+  out.y = __shfl_sync(FULL, mine, 8);
+  out.z = __shfl_sync(FULL, mine, 16);
+  out.w = __shfl_sync(FULL, mine, 24);
+  return out;
+}
+template <typename T, int W>
+__device__ __noinline__ uint4 subpel_err4_win_ni(const Search<T> &S, int tr, int tc, int hstep, unsigned validmask) {
+  return subpel_err4_win_body<T, W>(S, tr, tc, hstep, validmask);
+}
+template <typename T, int W>
+__device__ __forceinline__ uint4 subpel_err4_win(const Search<T> &S, int tr, int tc, int hstep, unsigned validmask) {
+  if constexpr (InlineSubpel<W>::value) return subpel_err4_win_body<T, W>(S, tr, tc, hstep, validmask);
+  else return subpel_err4_win_ni<T, W>(S, tr, tc, hstep, validmask);
+}
+
 __device__ __forceinline__ int clip_px(int v, int bd) {
   const int m = (1 << bd) - 1;
   return v < 0 ? 0 : (v > m ? m : v);
@@ -1173,7 +1409,8 @@ struct Subpel {
 template <typename T, int W>
 __device__ __forceinline__ unsigned check_better(Subpel<T, W> &sp, int r8, int c8, bool accurate, int *is_better) {
   if (!in_range(sp.lim, r8, c8)) return (unsigned)INT_MAX_;
-  const unsigned cost = accurate ? upsampled_err<T, W>(*sp.S, r8, c8, sp.bd, sp.tmp) : bilinear_err<T, W>(*sp.S, r8, c8);
+  const unsigned cost = accurate ? upsampled_err<T, W>(*sp.S, r8, c8, sp.bd, sp.tmp)
+                                 : (TF_SUBPEL_WIN ? subpel_err_win<T, W>(*sp.S, r8, c8, 1) : bilinear_err<T, W>(*sp.S, r8, c8));
   if (cost < sp.besterr) {
     sp.besterr = cost;
     sp.best.row = r8;
@@ -1189,7 +1426,7 @@ __device__ MV2 first_level(Subpel<T, W> &sp, MV2 t, int hstep, bool accurate) {
   unsigned left, right, up, down;
   // The batched pass pays off for the throughput-bound 16x16 searches; the latency-bound 32x32 search
   // is faster with four short passes than with one pass of four times the dependent work per lane.
-  if (accurate || W == 32) {
+  if (accurate || (W == 32 && !TF_S32_ERR4)) {
     left = check_better(sp, t.row, t.col - hstep, accurate, nullptr);
     right = check_better(sp, t.row, t.col + hstep, accurate, nullptr);
     up = check_better(sp, t.row - hstep, t.col, accurate, nullptr);
@@ -1198,7 +1435,7 @@ __device__ MV2 first_level(Subpel<T, W> &sp, MV2 t, int hstep, bool accurate) {
     // one pass for the four candidates, then check_better's comparisons in the reference's order
     const unsigned vm = (in_range(sp.lim, t.row, t.col - hstep) ? 1u : 0u) | (in_range(sp.lim, t.row, t.col + hstep) ? 2u : 0u) |
                         (in_range(sp.lim, t.row - hstep, t.col) ? 4u : 0u) | (in_range(sp.lim, t.row + hstep, t.col) ? 8u : 0u);
-    const uint4 c = bilinear_err4<T, W>(*sp.S, t.row, t.col, hstep, vm);
+    const uint4 c = TF_SUBPEL_WIN ? subpel_err4_win<T, W>(*sp.S, t.row, t.col, hstep, vm) : bilinear_err4<T, W>(*sp.S, t.row, t.col, hstep, vm);
     left = c.x, right = c.y, up = c.z, down = c.w;
     const int dr[4] = { 0, 0, -hstep, hstep }, dc[4] = { -hstep, hstep, 0, 0 };
     const unsigned cs[4] = { left, right, up, down };
@@ -1253,7 +1490,7 @@ __device__ void second_level_v2(Subpel<T, W> &sp, MV2 t, MV2 diag) {
 // av1_find_best_sub_pixel_tree{,_pruned,_pruned_more} (mcomp.c:2844-3133) with
 // cost_list == NULL, forced_stop = EIGHTH_PEL, MV_COST_NONE, unscaled refs.
 template <typename T, int W>
-__device__ __forceinline__ unsigned subpel_search_body(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+__device__ __forceinline__ unsigned subpel_search_body(Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
   Subpel<T, W> sp;
   sp.S = &S;
   sp.bd = P.is_hbd ? P.bit_depth : 8;
@@ -1277,8 +1514,13 @@ __device__ __forceinline__ unsigned subpel_search_body(const Search<T> &S, const
       hstep >>= 1;
     }
   } else {
+    // every candidate of the stage lies within two full-pel steps of its start: one window for all of them
+    if (TF_SUBPEL_WIN && !window_covers(S, start_full.row, start_full.col, 2))
+      window_load<T, W>(S, reinterpret_cast<unsigned char *>(tmp), start_full.row, start_full.col);
     // setup_center_error (mcomp.c:2718-2777): vf(ref, src); the variance is symmetric in its arguments
-    if constexpr (VAR_VIA_SUBPEL_ROUTINE) {
+    if constexpr (TF_SUBPEL_WIN != 0) {
+      sp.besterr = subpel_err_win<T, W>(S, start.row, start.col, 2);
+    } else if constexpr (VAR_VIA_SUBPEL_ROUTINE) {
       sp.besterr = bilinear_err<T, W>(S, start.row, start.col, 2);
     } else {
       unsigned sse;
@@ -1298,11 +1540,11 @@ __device__ __forceinline__ unsigned subpel_search_body(const Search<T> &S, const
 }
 
 template <typename T, int W>
-__device__ __noinline__ unsigned subpel_search_ni(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+__device__ __noinline__ unsigned subpel_search_ni(Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
   return subpel_search_body<T, W>(S, P, start_full, best, tmp);
 }
 template <typename T, int W>
-__device__ __forceinline__ unsigned subpel_search(const Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+__device__ __forceinline__ unsigned subpel_search(Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
   if constexpr (InlineSubpel<W>::value) return subpel_search_body<T, W>(S, P, start_full, best, tmp);
   else return subpel_search_ni<T, W>(S, P, start_full, best, tmp);
 }
@@ -1324,6 +1566,7 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
   S.hbd_shift = P.hbd_shift;
   S.is_hbd = P.is_hbd;
   S.win = nullptr;
+  S.srcs = 0;
   S.wr = S.wc = S.wR = S.wpitch = S.wshift = 0;
   S.ctr = P.ctr;
   // av1_set_mv_{row,col}_limits (mcomp.h:216-240) + av1_set_mv_search_range (mcomp.c:196-215)
@@ -1371,6 +1614,7 @@ __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_cons
   Search<T> S;
   search_init(S, P, mb_row, mb_col);
   S.src = cur + y_offset;
+  src_tile_load<T, 32>(S, smem_raw + SearchSmem<T, 32>::WIN);  // once per block: the same source for every frame
   // ref_mv chain (temporal_filter.c:855-871): carried in global memory across launches
   MV2 ref_mv = { 0, 0 };
   if (P.frame_begin > 0) {
@@ -1443,6 +1687,7 @@ __global__ void __launch_bounds__(32, S16_WARPS) tf_search16_kernel(const __grid
   search_init(S, P, mb_row, mb_col);
   S.src = reinterpret_cast<const T *>(P.frm[P.filter_idx][0]) + off;
   S.ref = reinterpret_cast<const T *>(P.frm[frame][0]) + off;
+  src_tile_load<T, 16>(S, smem_raw + SearchSmem<T, 16>::WIN);
   const size_t bf = (size_t)blk * P.num_frames + frame;
   const MV2 start = { rawpel((int)P.s_blk_mv[bf * 2 + 0]), rawpel((int)P.s_blk_mv[bf * 2 + 1]) };
   MV2 best_full, best;

@@ -354,7 +354,7 @@ def main():
                     help="CPU reference flavour: auto = AVX2-bound build when the host has AVX2, c = generic C")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--concurrent", type=int, default=0,
-                    help="independent windows in flight per GPU (contexts); 0 = auto: 2 for 4K, 4 below")
+                    help="independent windows in flight per GPU (contexts); 0 = auto: 3 for 4K, 4 below")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "tfgpu" else args.warmup
     wl = args.workload
@@ -381,7 +381,7 @@ def main():
     sharding = importlib.import_module("aom_av1_psy_b200.sharding")
     width, height, bd, n, strength = WORKLOADS[wl]
     slab_req = args.mode == "slab" and world > 1
-    conc = args.concurrent if args.concurrent > 0 else (1 if slab_req else (2 if width >= 3000 else 4))
+    conc = args.concurrent if args.concurrent > 0 else (1 if slab_req else (3 if width >= 3000 else 4))
     ctxs = [pkg.TemporalFilterGpu(device=local, max_cached_frames=40) for _ in range(conc)]
     ctx = ctxs[0]
 
@@ -695,7 +695,9 @@ def main():
     shares = {"tf_search32_kernel": kt[0], "tf_filter_kernel": kt[2]}
     dom_name = max(shares, key=shares.get)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(wl, {}).get(dom_name)
     achieved = alg_bytes[dom_name] / (per_launch_ms[dom_name] * 1e-3) / 1e9

@@ -71,7 +71,7 @@ for kname in ("tf_search32", "tf_search16", "tf_filter"):
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
     traffic[kname + "_kernel"] = num('dram__bytes_read.sum') + num('dram__bytes_write.sum')
 if traffic:
-    p = os.path.join(out, "traffic_r01.json")
+    p = os.path.join(out, f"traffic_{R}.json")
     cur = json.load(open(p)) if os.path.exists(p) else {}
     cur.setdefault(WLNAME, {}).update(traffic)
     cur["_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full (per-frame launches for the search kernels)"

@@ -12,7 +12,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 width, height, bd, n, strength = bench.WORKLOADS[wl]
 pkg = bench.load_package()
 ctx = pkg.TemporalFilterGpu(device=0, max_cached_frames=40)
-p = _params.tf_params(width, height, n, bit_depth=bd, q_factor=bench.Q_FACTOR, filter_strength=strength)
+p = bench.window_params(wl)  # the parameters of the bench line (q, allow_hp from the aomenc run)
 frames = bench.make_window(width, height, bd, n, 77 if bd > 8 else 1234)
 bufs = []
 for i, (y, u, v) in enumerate(frames):
