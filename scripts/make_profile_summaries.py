@@ -51,7 +51,7 @@ for kname in ("tf_search32", "tf_search16", "tf_filter"):
         open("/tmp/_cs.csv", "w").write(cs)
         f.write("\n# by source function (instructions / stall samples)\n")
         f.write(subprocess.run([sys.executable, os.path.join(root, "scripts", "ncu_by_function.py"), "/tmp/_cs.csv",
-                                os.path.join(root, "aom-av1-psy_b200/csrc/tf_kernels.cuh"), "12"], capture_output=True, text=True).stdout)
+                                os.environ.get("TF_KERNELS_SRC", os.path.join(root, "aom-av1-psy_b200/csrc/tf_kernels.cuh")), "12"], capture_output=True, text=True).stdout)
         s = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
         srows = list(csv.reader(s.splitlines()))
         sh = srows[1]
