@@ -99,10 +99,12 @@ struct tf_gpu_ctx {
   unsigned long long *d_ctr = nullptr;    // [4] executed-work counters (instrumentation)
   unsigned long long h_ctr[4] = { 0, 0, 0, 0 };
   bool collect_counters = false;
-  // development switches (environment, read once at create): TF_GPU_S16=single launches the 16x16 searches of
+  // development switches (environment, read once at create): TF_GPU_CHAIN=fused|frames overrides the choice of
+  // the latency mode in launch_filter(); TF_GPU_S16=single launches the 16x16 searches of
   // all frames as one grid after the chain instead of one grid per frame; TF_GPU_PRIO=flat gives every stream
   // the same priority
-  bool s16_single_launch = false;
+  int s16_mode = 0;  // TF_GPU_S16: 1 = single launch after the chain, otherwise one launch per frame
+  int chain_mode = 0;  // TF_GPU_CHAIN: 0 = auto (fused for row-range calls resident in one wave), 1 = fused, 2 = per frame
   unsigned long long *h_noise = nullptr;
   Ticket tickets[8];
   uint64_t next_ticket = 1;
@@ -510,7 +512,34 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   // chain), the independent 16x16 searches of that frame on a second stream as soon as its
   // 32x32 results exist -> the throughput-bound 16x16 work fills the latency-bound chain.
   int nlaunch = 0;
-  if (nref > 0) {
+  // Latency mode (a block-row slab of a frame whose blocks are resident at once): the per-frame launches make
+  // every frame wait for the slowest block of the previous one although a block only depends on itself
+  // (ref_mv); one search32 launch walks all frames of its block instead (time = the slowest block's total, not
+  // the sum of the per-frame maxima), followed by one search16 launch over all frames.
+  const bool row_range = (K.row_end - K.row_begin) < K.mb_rows;
+  const bool fused_chain = nref > 0 && grid <= ctx->num_sms * S32_WARPS_LO &&
+                           (ctx->chain_mode == 1 || (ctx->chain_mode == 0 && row_range));
+  if (fused_chain) {
+    for (int f = 0; f < p->num_frames; f++)
+      if (f != p->filter_frame_idx) CU(cudaStreamWaitEvent(ctx->stream, frames[f]->ready, 0));
+    KParams Kf = K;
+    Kf.frame_begin = 0;
+    Kf.frame_end = p->num_frames;
+    if (g.is_hbd) tf_search32_kernel<uint16_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
+    else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
+    nlaunch++;
+    if (timed) cudaEventRecord(te->evk[0], ctx->stream);
+    if (!p->force_integer_mv) {
+      if (g.is_hbd) tf_search16_kernel<uint16_t><<<grid * 4 * nref, 32, SearchSmem<uint16_t, 16>::TOTAL, ctx->stream>>>(Kf);
+      else tf_search16_kernel<uint8_t><<<grid * 4 * nref, 32, SearchSmem<uint8_t, 16>::TOTAL, ctx->stream>>>(Kf);
+      nlaunch++;
+    }
+    if (timed) cudaEventRecord(te->evk[1], ctx->stream);
+  } else if (nref > 0) {
+    // (one search16 launch over all frames after the chain instead: 4K 10-bit with three windows in flight
+    // 62.6 -> 63.6 frames/s, 1080p 329 -> 321, and a single window loses the overlap with its own chain: not the
+    // default)
+    const bool s16_single = ctx->s16_mode == 1;
     bool any16 = false;
     for (int f = 0; f < p->num_frames; f++) {
       if (f == p->filter_frame_idx) continue;
@@ -532,7 +561,7 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
         else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
       }
       nlaunch++;
-      if (!p->force_integer_mv && !ctx->s16_single_launch) {
+      if (!p->force_integer_mv && !s16_single) {
         CU(cudaEventRecord(ctx->ev_f32[f], ctx->stream));
         CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_f32[f], 0));
         Kf.frame_begin = f;
@@ -547,7 +576,7 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
       }
     }
     if (timed) cudaEventRecord(te->evk[0], ctx->stream);
-    if (!p->force_integer_mv && ctx->s16_single_launch) {
+    if (!p->force_integer_mv && s16_single) {
       KParams K16 = K;
       K16.frame_begin = 0;
       K16.frame_end = p->num_frames;
@@ -767,7 +796,9 @@ int tf_gpu_create(tf_gpu_ctx **out, const tf_gpu_device_cfg *cfg) {
   if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   {
     const char *m = getenv("TF_GPU_S16");
-    ctx->s16_single_launch = m && strcmp(m, "single") == 0;
+    ctx->s16_mode = m && strcmp(m, "single") == 0 ? 1 : (m && strcmp(m, "frames") == 0 ? 2 : 0);
+    const char *cm = getenv("TF_GPU_CHAIN");
+    ctx->chain_mode = cm && strcmp(cm, "fused") == 0 ? 1 : (cm && strcmp(cm, "frames") == 0 ? 2 : 0);
     const char *pr = getenv("TF_GPU_PRIO");
     if (pr && strcmp(pr, "flat") == 0) prio_hi = prio_lo;
     // TF_GPU_CARVEOUT=<percent>: preferred shared-memory carveout of the search kernels (development switch)
