@@ -32,6 +32,7 @@ EXPORTS = [
     "tf_gpu_host_register", "tf_gpu_host_unregister", "tf_gpu_last_stats", "tf_gpu_event_record",
     "tf_gpu_event_elapsed_ms", "tf_gpu_synchronize", "tf_gpu_microbench", "tf_gpu_last_kernel_times", "tf_gpu_filter_resident_async", "tf_gpu_filter_resident_result", "tf_gpu_collect_counters", "tf_gpu_read_counters",
     "tf_gpu_cache_frame_async", "tf_gpu_debug_read_plane", "tf_gpu_device_border", "tf_gpu_fullpel_search_batch",
+    "tf_gpu_output_ipc_export", "tf_gpu_output_ipc_import",
 ]
 
 
@@ -109,6 +110,8 @@ def load_library():
     lib.tf_gpu_cache_frame_async.argtypes = [vp, C.POINTER(Frame)]
     lib.tf_gpu_debug_read_plane.argtypes = [vp, u64, i, vp, i, i, i, i, i]
     lib.tf_gpu_device_border.restype = i
+    lib.tf_gpu_output_ipc_export.argtypes = [vp, i, C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.tf_gpu_output_ipc_import.argtypes = [vp, i, C.c_char_p, C.c_size_t, C.c_size_t]
     lib.tf_gpu_fullpel_search_batch.argtypes = [vp, C.POINTER(Params), C.POINTER(Frame), C.POINTER(Frame), i,
                                                 C.POINTER(SearchItem), i, C.POINTER(SearchResult)]
     lib.tf_gpu_filter_resident.argtypes = [vp, C.POINTER(Params), C.POINTER(u64), C.POINTER(C.c_int64),
@@ -364,6 +367,17 @@ class TemporalFilterGpu:
         self._check(self.lib.tf_gpu_output_device_plane(self.h, plane, C.byref(p), C.byref(pitch), C.byref(rows),
                                                         C.byref(rb)))
         return p.value, pitch.value, rows.value, rb.value
+
+    def output_ipc_export(self, plane):
+        """(handle bytes, byte offset of pixel (0,0), pitch bytes) of an output plane, for another rank's import."""
+        buf = C.create_string_buffer(64)
+        off, pitch = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.tf_gpu_output_ipc_export(self.h, plane, buf, C.byref(off), C.byref(pitch)))
+        return buf.raw, off.value, pitch.value
+
+    def output_ipc_import(self, plane, handle, offset=0, pitch=0):
+        """Store this context's output rows into another rank's plane (handle=None: back to its own planes)."""
+        self._check(self.lib.tf_gpu_output_ipc_import(self.h, plane, handle, offset, pitch))
 
     def host_register(self, arr):
         self._check(self.lib.tf_gpu_host_register(self.h, arr.ctypes.data, arr.nbytes))

@@ -94,6 +94,10 @@ struct tf_gpu_ctx {
   DevFrame out;
   uint64_t use_counter = 0, epoch = 0;
   unsigned long long *d_diff = nullptr;   // [9][2]: one slot per ticket, slot 8 = resident path
+  // slab mode over peer memory: another rank's output planes opened through CUDA IPC (tf_gpu_output_ipc_import)
+  void *peer_base[3] = { nullptr, nullptr, nullptr };
+  void *peer_out[3] = { nullptr, nullptr, nullptr };
+  size_t peer_pitch[3] = { 0, 0, 0 };
   unsigned long long *h_diff = nullptr;   // pinned mirror
   unsigned long long *d_noise = nullptr;  // [2]
   unsigned long long *d_ctr = nullptr;    // [4] executed-work counters (instrumentation)
@@ -459,7 +463,14 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   }
   for (int f = 0; f < p->num_frames; f++)
     for (int pl = 0; pl < p->num_planes; pl++) K.frm[f][pl] = frames[f]->p00[pl];
-  for (int pl = 0; pl < p->num_planes; pl++) K.out[pl] = ctx->out.p00[pl];
+  for (int pl = 0; pl < p->num_planes; pl++) {
+    K.out[pl] = ctx->out.p00[pl];
+    if (ctx->peer_out[pl]) {  // the owner rank's plane: same geometry, hence the same pitch
+      if (ctx->peer_pitch[pl] != (size_t)ctx->out.g.pitch[pl > 0] * (g.is_hbd ? 2 : 1))
+        return fail(ctx, TF_GPU_ERR_INVALID, "imported output plane %d has a different pitch than this context's", pl);
+      K.out[pl] = ctx->peer_out[pl];
+    }
+  }
   K.diff = d_diff;
   K.ctr = nullptr;
   if (ctx->collect_counters) {
@@ -517,7 +528,8 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
   // (ref_mv); one search32 launch walks all frames of its block instead (time = the slowest block's total, not
   // the sum of the per-frame maxima), followed by one search16 launch over all frames.
   const bool row_range = (K.row_end - K.row_begin) < K.mb_rows;
-  const bool fused_chain = nref > 0 && grid <= ctx->num_sms * S32_WARPS_LO &&
+  const int hi_warps = g.is_hbd ? S32_WARPS_HI_HBD : S32_WARPS_HI;
+  const bool fused_chain = nref > 0 && grid <= ctx->num_sms * hi_warps &&
                            (ctx->chain_mode == 1 || (ctx->chain_mode == 0 && row_range));
   if (fused_chain) {
     for (int f = 0; f < p->num_frames; f++)
@@ -525,8 +537,14 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     KParams Kf = K;
     Kf.frame_begin = 0;
     Kf.frame_end = p->num_frames;
-    if (g.is_hbd) tf_search32_kernel<uint16_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
-    else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
+    const bool dense = grid > ctx->num_sms * S32_WARPS_LO;  // resident at once only with the denser build
+    if (g.is_hbd) {
+      if (dense) tf_search32_kernel<uint16_t, S32_WARPS_HI_HBD><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
+      else tf_search32_kernel<uint16_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
+    } else {
+      if (dense) tf_search32_kernel<uint8_t, S32_WARPS_HI><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
+      else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
+    }
     nlaunch++;
     if (timed) cudaEventRecord(te->evk[0], ctx->stream);
     if (!p->force_integer_mv) {
@@ -880,6 +898,8 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
     if (ctx->out.base[p]) cudaFree(ctx->out.base[p]);
   for (int i = 0; i < 12; i++)
     if (ctx->d_dump[i]) cudaFree(ctx->d_dump[i]);
+  for (int p = 0; p < 3; p++)
+    if (ctx->peer_base[p]) cudaIpcCloseMemHandle(ctx->peer_base[p]);
   if (ctx->d_diff) cudaFree(ctx->d_diff);
   if (ctx->h_diff) cudaFreeHost(ctx->h_diff);
   if (ctx->d_noise) cudaFree(ctx->d_noise);
@@ -1131,6 +1151,40 @@ int tf_gpu_output_device_plane(tf_gpu_ctx *ctx, int plane, void **dptr, size_t *
   if (pitch_bytes) *pitch_bytes = (size_t)g.pitch[k] * es;
   if (rows) *rows = ((g.crop_h[0] + 31) / 32) * (32 >> (plane ? g.ss_y : 0));
   if (row_bytes) *row_bytes = (int)(((g.crop_w[0] + 31) / 32) * (32 >> (plane ? g.ss_x : 0)) * es);
+  return TF_GPU_OK;
+}
+
+int tf_gpu_output_ipc_export(tf_gpu_ctx *ctx, int plane, unsigned char handle[TF_GPU_IPC_HANDLE_BYTES], size_t *offset_bytes,
+                             size_t *pitch_bytes) {
+  if (!ctx || !handle || plane < 0 || plane > 2) return TF_GPU_ERR_INVALID;
+  if (!ctx->out.base[plane]) return fail(ctx, TF_GPU_ERR_INVALID, "no output plane %d on the device yet", plane);
+  static_assert(sizeof(cudaIpcMemHandle_t) == TF_GPU_IPC_HANDLE_BYTES, "handle size");
+  CU(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->out.base[plane]));
+  memcpy(handle, &h, sizeof(h));
+  if (offset_bytes) *offset_bytes = (size_t)((char *)ctx->out.p00[plane] - (char *)ctx->out.base[plane]);
+  if (pitch_bytes) *pitch_bytes = (size_t)ctx->out.g.pitch[plane > 0] * (ctx->out.g.is_hbd ? 2 : 1);
+  return TF_GPU_OK;
+}
+
+int tf_gpu_output_ipc_import(tf_gpu_ctx *ctx, int plane, const unsigned char *handle, size_t offset_bytes, size_t pitch_bytes) {
+  if (!ctx || plane < 0 || plane > 2) return TF_GPU_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));  // no kernel may still be writing through the old mapping
+  if (ctx->peer_base[plane]) {
+    CU(cudaIpcCloseMemHandle(ctx->peer_base[plane]));
+    ctx->peer_base[plane] = ctx->peer_out[plane] = nullptr;
+    ctx->peer_pitch[plane] = 0;
+  }
+  if (!handle) return TF_GPU_OK;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void *base = nullptr;
+  CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  ctx->peer_base[plane] = base;
+  ctx->peer_out[plane] = (char *)base + offset_bytes;
+  ctx->peer_pitch[plane] = pitch_bytes;
   return TF_GPU_OK;
 }
 

@@ -7,7 +7,9 @@ Two independent axes, no exchange during compute:
     a halo smaller than the frame cannot be bit-exact) and computes only its
     output rows (tf_gpu_params.out_row_begin/end), which are then gathered to
     rank 0 straight from the library's device output planes, plus a 16-byte
-    all-reduce for FRAME_DIFF (integer sums: order independent).
+    all-reduce for FRAME_DIFF (integer sums: order independent); or, without any
+    gather, every rank stores its rows straight into rank 0's planes over NVLink
+    (CUDA IPC peer mapping, `connect_peer_output`).
 The reference's counterpart is the row job queue of av1/encoder/ethread.c:2062-2189
 (workers share tf_ctx->output_frame and add their FRAME_DIFF under a mutex, :2161-2173).
 
@@ -72,6 +74,51 @@ class SlabWindow:
             lo = self.begin * bh * pitch
             out.append(t[lo:lo + self.pad_rows * bh * pitch])
         return out
+
+    def device_planes(self, ctx, torch, device):
+        """The library's whole output planes (all block rows, whole pitched rows) as flat uint8 tensors."""
+        out = []
+        for pl, bh in enumerate(self.block_h):
+            ptr, pitch, rows, row_bytes = ctx.output_device_plane(pl)
+
+            class _View:
+                pass
+            v = _View()
+            v.__cuda_array_interface__ = {"shape": (self.mb_rows * bh * pitch,), "typestr": "|u1",
+                                          "data": (ptr, False), "version": 3}
+            out.append(torch.as_tensor(v, device=device))
+        return out
+
+    # ---- peer-store variant: no gather, every rank writes its rows into the owner's planes over NVLink -------
+    def connect_peer_output(self, ctx, dist, owner=0):
+        """The owner exports its device output planes (CUDA IPC), every other rank imports them: from now on a
+        rank's filter call stores its block rows straight into the owner's frame (tf_gpu_output_ipc_*).  The
+        owner's planes must exist (one filter call of this geometry has run on every rank)."""
+        box, err = [None], None
+        if self.rank == owner:
+            try:
+                box = [[ctx.output_ipc_export(pl) for pl in range(len(self.block_h))]]
+            except Exception as e:  # the broadcast below still has to happen on every rank
+                err = e
+        dist.broadcast_object_list(box, src=owner)
+        if err is not None:
+            raise err
+        if box[0] is None:
+            raise RuntimeError("the owner rank could not export its output planes")
+        if self.rank != owner:
+            for pl, (handle, off, pitch) in enumerate(box[0]):
+                ctx.output_ipc_import(pl, handle, off, pitch)
+
+    def disconnect_peer_output(self, ctx, owner=0):
+        if self.rank != owner:
+            for pl in range(len(self.block_h)):
+                ctx.output_ipc_import(pl, None)
+
+    def finish_peer(self, diff, dist):
+        """After this rank's filter call has completed: sum FRAME_DIFF over the ranks; past this all-reduce every
+        rank's rows are in the owner's planes."""
+        dist.all_reduce(diff)
+        return diff
 
     # ---- collective ---------------------------------------------------------------------------
     def gather(self, slabs, diff, dist, torch):

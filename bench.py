@@ -599,7 +599,58 @@ def main():
                 bad = int((got != want).sum()) if got.shape == want.shape else -1
                 detail["mismatching_samples"].append(bad)
                 ok = ok and bad == 0
+        # ---- the same slabs without a gather: every rank stores its rows into rank 0's planes over NVLink ----
+        peer = None
+        try:
+            perr = None
+            try:
+                sw.connect_peer_output(ctx, dist)
+            except Exception as e:
+                perr = e
+            pflag = torch.tensor([0.0 if perr is None else 1.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(pflag, op=dist.ReduceOp.MAX)  # every rank takes the same branch
+            if pflag.item() > 0:
+                sw.disconnect_peer_output(ctx)
+                raise RuntimeError(f"peer mapping failed on some rank ({perr!r})")
+            if rank == 0:
+                for t in sw.device_planes(ctx, torch, dev):
+                    t.zero_()  # what is compared below can only have come from the timed steps
+                torch.cuda.synchronize()
+            plast = {}
+
+            def pstep():
+                ctx.filter_resident_async(ps, sids)
+                _, diff = ctx.filter_resident_result()
+                plast["d"] = sw.finish_peer(torch.from_numpy(diff.copy()).to(dev), dist)
+                torch.cuda.current_stream().synchronize()
+
+            for _ in range(3):
+                pstep()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(nsteps):
+                pstep()
+            barrier()
+            pwall = (time.perf_counter() - t0) * 1e3 / nsteps
+            tp = torch.tensor([pwall], device=dev, dtype=torch.float64)
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            pwall = tp.item()
+            pok = None
+            if rank == 0:
+                ctx.download_output(vout)
+                pok = bool((plast["d"].cpu().numpy() == full_diff).all())
+                for pl in range(3):
+                    pok = pok and bool((vout.full_blocks(pl) == full_planes[pl]).all())
+            barrier()
+            sw.disconnect_peer_output(ctx)
+            peer = {"mode": "no gather: every rank stores its block rows into rank 0's output planes over NVLink "
+                            "(CUDA IPC peer mapping, tf_gpu_output_ipc_export/import) + 16-byte all-reduce of FRAME_DIFF",
+                    "ms_per_frame": pwall, "frames_per_sec": 1e3 / pwall, "speedup": t_one_max / pwall,
+                    "efficiency": t_one_max / pwall / world, "verified": pok}
+        except Exception as e:  # no peer access between the GPUs of this box: the NCCL figures above stand
+            peer = {"unavailable": repr(e)[:200]}
         return {"mode": "block-row slabs of one window per GPU + NCCL gather to rank 0 (SlabWindow)",
+                "peer_store": peer,
                 "ms_per_frame": wall, "frames_per_sec": 1e3 / wall, "single_gpu_ms_per_frame": t_one_max,
                 "speedup": t_one_max / wall, "efficiency": t_one_max / wall / world,
                 "gather_ms": g_ms, "search32_chain_ms": c_ms, "steps": nsteps, "clocks": clk, "verified": ok,

@@ -190,6 +190,22 @@ int tf_gpu_download_output(tf_gpu_ctx *ctx, tf_gpu_frame *out, int row_begin, in
 int tf_gpu_output_device_plane(tf_gpu_ctx *ctx, int plane, void **dptr, size_t *pitch_bytes,
                                int *rows, int *row_bytes);
 
+/* Slab mode over peer memory (one process per GPU on one NVLink / NVSwitch box): the rank that owns the output
+ * frame exports its device output planes as CUDA IPC handles; the other ranks import them, and from then on their
+ * filter calls store their block rows (out_row_begin/end) straight into the owner's planes over NVLink -- the
+ * shared tf_ctx->output_frame all row workers of the reference write (ethread.c:2083-2108), with no gather step.
+ * A rank's stores are visible to the owner once its call has completed (tf_gpu_filter_resident_result /
+ * tf_gpu_wait) and any inter-process synchronisation (e.g. the FRAME_DIFF all-reduce) has been passed.
+ * export: valid after the first filter call of that geometry (the planes exist); handle = 64 opaque bytes
+ * (cudaIpcMemHandle_t), offset = byte offset of pixel (0, 0) from the allocation base.
+ * import: handle == NULL closes the mapping and returns to the context's own planes; pitch_bytes must equal the
+ * importing context's own output pitch for that plane (same frame geometry), checked at the next filter call. */
+#define TF_GPU_IPC_HANDLE_BYTES 64
+int tf_gpu_output_ipc_export(tf_gpu_ctx *ctx, int plane, unsigned char handle[TF_GPU_IPC_HANDLE_BYTES],
+                             size_t *offset_bytes, size_t *pitch_bytes);
+int tf_gpu_output_ipc_import(tf_gpu_ctx *ctx, int plane, const unsigned char *handle, size_t offset_bytes,
+                             size_t pitch_bytes);
+
 /* First consumer beyond the temporal filter: the full-pixel search engine as a batch call.
  * Every item is one block of `src` at luma position (x, y) searched in `ref` from a full-pel start MV with
  * av1_full_pixel_search() (mcomp.c:1693-1832; NSTEP sites, cost_list == NULL) configured as tf_motion_search()

@@ -1,7 +1,8 @@
 """GPU, 2 ranks, NCCL: the slab-parallel path of BASELINE.json config 4 as bench.py runs it -- one process per
 GPU, every rank filters its block-row range of the same window through the library's row-range mode,
 sharding.SlabWindow gathers the slabs from the library's device output planes to rank 0 over NCCL and all-reduces
-FRAME_DIFF.  The gathered frame must equal the frame one GPU computes alone, bit for bit, and the oracle's rows.
+FRAME_DIFF.  The gathered frame must equal the frame one GPU computes alone, bit for bit, and the oracle's rows;
+so must the frame assembled without a gather, by every rank storing its rows into rank 0's planes (CUDA IPC peer mapping).
 Needs two GPUs (run with `gpurun --gpus 2`); skipped on a one-GPU box."""
 import os
 import sys
@@ -72,6 +73,30 @@ def _worker(rank, world, port, case, q):
                     ok = ok and bool((got.astype(np.uint16) == want).all())
         else:
             assert g is None
+    # the same slabs without a gather: every rank stores its rows into rank 0's planes over NVLink (CUDA IPC)
+    sw.connect_peer_output(ctx, dist)
+    if rank == 0:
+        for t in sw.device_planes(ctx, torch, "cuda:0"):
+            t.zero_()
+        torch.cuda.synchronize()
+    dist.barrier()
+    _, diff = ctx.filter_resident(sw.params(p), ids)
+    dsum = sw.finish_peer(torch.from_numpy(diff.copy()).to(f"cuda:{rank}"), dist)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        got = pkg.Yv12Buffer(W, H, 1, 1, bd > 8, p["border"])
+        ctx.download_output(got)
+        sw.disconnect_peer_output(ctx)
+        _, full_diff = ctx.filter_resident(dict(p, out_row_begin=0, out_row_end=0), ids)
+        ref = pkg.Yv12Buffer(W, H, 1, 1, bd > 8, p["border"])
+        ctx.download_output(ref)
+        ok = ok and bool((dsum.cpu().numpy() == full_diff).all())
+        for pl in range(3):
+            ok = ok and bool((got.full_blocks(pl) == ref.full_blocks(pl)).all())
+    else:
+        sw.disconnect_peer_output(ctx)
+    dist.barrier()
     if rank == 0:
         q.put(ok)
     ctx.close()
