@@ -27,36 +27,17 @@
 namespace tfk {
 
 constexpr unsigned FULL = 0xffffffffu;
-// TF_S32_ERR4: the 32x32 search evaluates the four first-level sub-pel candidates in one batched pass like the
-// 16x16 search (fewer instructions, longer dependent chain per warp).
-#ifndef TF_S32_ERR4
-#define TF_S32_ERR4 1
-#endif
 // TF_FILT_WUNROLL: unroll factor of the weight loop of the filter kernel (0 = full, the co-located luma sums
 // of the chroma planes precomputed in registers).  Not unrolled: the filter kernel shrinks from 64 to 40 KB of
 // code (its instruction-cache request rate was 89% of peak) and loses its spills: 2.85 -> 2.65 ms at 4K 10-bit.
 #ifndef TF_FILT_WUNROLL
 #define TF_FILT_WUNROLL 1
 #endif
-// Inlining policy of the search routines.  A routine that is not inlined into the kernel re-materialises the
-// global-memory descriptor for each of its loads (LDC + 2 x R2UR per LDG: 10% of the executed instructions
-// of both search kernels in the round-1 build) and passes its context through the stack.
-#ifndef TF_NI_SEARCH
-#define TF_NI_SEARCH __forceinline__
-#endif
-// Sub-pel / variance routines (many call sites): inlined as well (16x16 search: instruction-fetch stalls 12% -> 5%,
-// 548 -> 495 us per launch at 4K).  For the 32x32 search inlining only pays together with the batched first-level
-// pass (TF_S32_ERR4: four out-of-line calls become one inlined pass): 60.4 -> 61.5 frames/s at 4K 10-bit.
-#ifndef TF_INLINE_SUBPEL_W16
-#define TF_INLINE_SUBPEL_W16 1
-#endif
-#ifndef TF_INLINE_SUBPEL_W32
-#define TF_INLINE_SUBPEL_W32 1
-#endif
-template <int W>
-struct InlineSubpel {
-  static constexpr bool value = (W == 16) ? (TF_INLINE_SUBPEL_W16 != 0) : (TF_INLINE_SUBPEL_W32 != 0);
-};
+// Inlining policy: every search routine is inlined into its kernel.  A routine that is not inlined re-materialises
+// the global-memory descriptor for each of its loads (LDC + 2 x R2UR per LDG: 10% of the executed instructions of
+// both search kernels in the round-1 build) and passes its context through the stack; the out-of-line routines
+// were a round-1 answer to the instruction-fetch stalls of one fused kernel, and with three kernels inlining
+// lowers them instead (16x16 search: no_inst 12% -> 5%).  Only the 8-tap routine of SUBPEL_TREE stays out of line.
 constexpr int MAXF = 24;
 constexpr int INT_MAX_ = 0x7fffffff;
 
@@ -247,7 +228,7 @@ __device__ __forceinline__ void src_tile_load(Search<T> &S, unsigned char *buf) 
 
 // Cooperative, coalesced window fill: 16-byte global loads, 4-byte shared stores.
 template <typename T, int W>
-__device__ TF_NI_SEARCH void window_load(Search<T> &S, unsigned char *buf, int wr, int wc) {
+__device__ __forceinline__ void window_load(Search<T> &S, unsigned char *buf, int wr, int wc) {
   using C = WinCfg<T, W>;
   const int lane = lane_id();
   const T *g0 = S.ref + (wr - C::R) * S.stride + (wc - C::R);
@@ -524,8 +505,7 @@ __device__ __forceinline__ unsigned var_finish(int sum, unsigned long long sse, 
 }
 
 template <typename T, int W>
-__device__ __forceinline__ unsigned variance_body(const T *a, int as, const T *b, int bs, int hbd_shift,
-                                                  unsigned *sse_out) {
+__device__ __forceinline__ unsigned variance(const T *a, int as, const T *b, int bs, int hbd_shift, unsigned *sse_out) {
   const int lane = lane_id();
   constexpr int RP = 32 / W;  // rows per iteration
   const int col = lane % W, r0 = lane / W;
@@ -539,15 +519,6 @@ __device__ __forceinline__ unsigned variance_body(const T *a, int as, const T *b
   }
   const unsigned long long sse64 = warp_sum_pair(sum, sse);
   return var_finish(sum, sse64, W, hbd_shift, sse_out);
-}
-template <typename T, int W>
-__device__ __noinline__ unsigned variance_ni(const T *a, int as, const T *b, int bs, int hbd_shift, unsigned *sse_out) {
-  return variance_body<T, W>(a, as, b, bs, hbd_shift, sse_out);
-}
-template <typename T, int W>
-__device__ __forceinline__ unsigned variance(const T *a, int as, const T *b, int bs, int hbd_shift, unsigned *sse_out) {
-  if constexpr (InlineSubpel<W>::value) return variance_body<T, W>(a, as, b, bs, hbd_shift, sse_out);
-  else return variance_ni<T, W>(a, as, b, bs, hbd_shift, sse_out);
 }
 
 template <typename T, int W>
@@ -584,7 +555,7 @@ __device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
 // per-candidate code.
 // ---------------------------------------------------------------------------
 template <typename T, int W, bool SKIP>
-__device__ TF_NI_SEARCH unsigned diamond_search(const Search<T> &S_in, MV2 start, int search_step, int *num00,
+__device__ __forceinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start, int search_step, int *num00,
                                                 MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
   constexpr int PU = (W == 32) ? 2 : (L::MAXP < 3 ? L::MAXP : 3);  // passes whose loads are issued back to back
@@ -772,7 +743,7 @@ __device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param,
 // group keeps the best key (total << 32 | visit index) of the candidates it
 // evaluated and one warp min-reduction at the end picks the winner.
 template <typename T, int W, bool SKIP>
-__device__ TF_NI_SEARCH int mesh_search(const Search<T> &S_in, MV2 start, int range, int step, MV2 *best_out) {
+__device__ __forceinline__ int mesh_search(const Search<T> &S_in, MV2 start, int range, int step, MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
   constexpr int PU = 2;
   const Search<T> S = S_in;
@@ -873,7 +844,7 @@ __device__ int full_pixel_exhaustive(Search<T> &S, const KParams &P, MV2 start, 
 // Returns 1 when the skip-row result must be discarded and the search redone
 // with full SAD (mcomp.c:1777-1810).
 template <typename T, int W, bool SKIP>
-__device__ TF_NI_SEARCH int full_pixel_search_pass(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv,
+__device__ __forceinline__ int full_pixel_search_pass(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv,
                                                    unsigned char *winbuf) {
   int run_mesh = 1;
   int var = full_pixel_diamond<T, W, SKIP>(S, start, P.step_param, best_mv);
@@ -944,7 +915,7 @@ __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2
 // mode 2: full-pel variance vf(ref, src); mode 3: full-pel variance vf(src, ref) (difference negated).
 // Modes 2 and 3 count as variance work in the instrumentation.
 template <typename T, int W>
-__device__ __forceinline__ unsigned bilinear_err_body(const Search<T> &S_in, int r8, int c8, int mode) {
+__device__ __forceinline__ unsigned bilinear_err(const Search<T> &S_in, int r8, int c8, int mode) {
   const Search<T> S = S_in;
   const int lane = lane_id();
   const int fr = r8 >> 3, fc = c8 >> 3;
@@ -1022,129 +993,6 @@ __device__ __forceinline__ unsigned bilinear_err_body(const Search<T> &S_in, int
   return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
 }
 
-template <typename T, int W>
-__device__ __noinline__ unsigned bilinear_err_ni(const Search<T> &S, int r8, int c8, int mode) {
-  return bilinear_err_body<T, W>(S, r8, c8, mode);
-}
-template <typename T, int W>
-__device__ __forceinline__ unsigned bilinear_err(const Search<T> &S, int r8, int c8, int mode) {
-  if constexpr (InlineSubpel<W>::value) return bilinear_err_body<T, W>(S, r8, c8, mode);
-  else return bilinear_err_ni<T, W>(S, r8, c8, mode);
-}
-
-// The four first-level candidates of a sub-pel round (left, right, up, down of (tr, tc) at distance
-// hstep; first_level_check, mcomp.c:2503-2541) evaluated in one pass: their errors do not depend on the
-// incumbent, so the reference's sequential comparisons can be replayed on the four results afterwards.
-// Lane group g = lane / 8 evaluates candidate g; a lane owns one (W = 16) or two (W = 32) column pairs
-// over all rows, so there is no band overhead and one reduction / variance epilogue serves all four.
-// Candidates whose bit in validmask is clear are not read (their group re-reads the centre) and
-// return INT_MAX.  Same packed arithmetic as bilinear_err.
-template <typename T, int W>
-__device__ __forceinline__ uint4 bilinear_err4_body(const Search<T> &S_in, int tr, int tc, int hstep, unsigned validmask) {
-  const Search<T> S = S_in;
-  constexpr int ES = (int)sizeof(T);
-  constexpr int NP = W / 16;            // column pairs per lane
-  constexpr int CH = NP == 1 ? 8 : 4;   // rows per chunk: all loads of a chunk are issued before use
-  const int lane = lane_id(), g = lane >> 3, u = lane & 7;
-  const bool valid = (validmask >> g) & 1u;
-  int r8 = tr, c8 = tc;
-  if (valid) {
-    if (g == 0) c8 -= hstep;
-    else if (g == 1) c8 += hstep;
-    else if (g == 2) r8 -= hstep;
-    else r8 += hstep;
-  }
-  const int fr = r8 >> 3, fc = c8 >> 3;
-  const unsigned xo = c8 & 7, yo = r8 & 7;
-  // all four candidates and their +1 row / column lie within one full-pel step of the centre
-  const SadSrc Q = sad_src(S, window_covers(S, tr >> 3, tc >> 3, 2));
-  const uintptr_t a = reinterpret_cast<uintptr_t>(Q.base + fr * Q.pitchB + (fc + 2 * u) * ES);
-  const unsigned char *wb = reinterpret_cast<const unsigned char *>(a & ~(uintptr_t)3);
-  const unsigned sh = (unsigned)(a & 3) * 8;  // 16 pairs further on is a multiple of 4 bytes: same shift
-  const int sstep = S.stride / 2;
-  const unsigned m0 = 8 - xo, m1 = xo, n0 = 8 - yo, n1 = yo;
-  constexpr unsigned RND = 0x00040004u, MSK = 0x1fff1fffu;
-  auto hrow = [&](uint32_t w0, uint32_t w1) -> unsigned {
-    unsigned A, B;
-    if (ES == 2) {
-      A = __funnelshift_rc(w0, w1, sh);
-      B = __funnelshift_rc(w0, w1, sh + 16);
-    } else {
-      const unsigned x = __funnelshift_r(w0, w1, sh);
-      A = __byte_perm(x, 0, 0x4140);
-      B = __byte_perm(x, 0, 0x4241);
-    }
-    return ((A * m0 + (B * m1 + RND)) >> 3) & MSK;
-  };
-  auto src_pair = [&](int r, int p) -> unsigned {
-    if (ES == 2) return __ldg(reinterpret_cast<const uint32_t *>(S.src + 2 * (u + 8 * p)) + r * sstep);
-    const unsigned s = __ldg(reinterpret_cast<const uint16_t *>(S.src + 2 * (u + 8 * p)) + r * sstep);
-    return __byte_perm(s, 0, 0x4140);
-  };
-  unsigned hprev[NP];
-#pragma unroll
-  for (int p = 0; p < NP; p++) {
-    const uint32_t *wp = reinterpret_cast<const uint32_t *>(wb + p * 16 * ES);
-    hprev[p] = hrow(wp[0], wp[1]);
-  }
-  unsigned sumv = 0, sums = 0, accl = 0, acch = 0;
-#pragma unroll 1
-  for (int t0 = 0; t0 < W; t0 += CH) {
-    uint32_t w0[CH][NP], w1[CH][NP], sv[CH][NP];
-#pragma unroll
-    for (int k = 0; k < CH; k++)
-#pragma unroll
-      for (int p = 0; p < NP; p++) {
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(wb + (t0 + k + 1) * Q.pitchB + p * 16 * ES);
-        w0[k][p] = wp[0];
-        w1[k][p] = wp[1];
-      }
-#pragma unroll
-    for (int k = 0; k < CH; k++)
-#pragma unroll
-      for (int p = 0; p < NP; p++) sv[k][p] = src_pair(t0 + k, p);
-#pragma unroll
-    for (int k = 0; k < CH; k++)
-#pragma unroll
-      for (int p = 0; p < NP; p++) {
-        const unsigned hn = hrow(w0[k][p], w1[k][p]);
-        const unsigned v = ((hprev[p] * n0 + (hn * n1 + RND)) >> 3) & MSK;
-        hprev[p] = hn;
-        sumv = __dp2a_lo(v, 0x0101u, sumv);
-        sums = __dp2a_lo(sv[k][p], 0x0101u, sums);
-        const unsigned md = __vmaxu2(v, sv[k][p]) - __vminu2(v, sv[k][p]);
-        const unsigned pb = __byte_perm(md, 0, 0x3120);
-        accl = __dp2a_lo(md, pb, accl);
-        if (ES == 2) acch = __dp2a_hi(md, pb, acch);
-      }
-  }
-  if (S.ctr && lane == 0) atomicAdd(&S.ctr[1], (unsigned long long)(__popc(validmask & 15u) * W * W));
-  // (sum, sse) of a candidate = totals over its 8 lanes: |sum| < 2^19 per lane, so sum + 2^19 is
-  // non-negative and 8 of them stay below 2^24; sse totals < 2^35
-  unsigned long long pk = ((unsigned long long)(accl + (acch << 8)) << 24) | (unsigned)((int)sumv - (int)sums + (1 << 19));
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) pk += __shfl_xor_sync(FULL, pk, o);
-  const int sum = (int)(pk & 0xffffffu) - (1 << 22);
-  unsigned sse_out;
-  const unsigned mine = valid ? var_finish(sum, pk >> 24, W, S.hbd_shift, &sse_out) : (unsigned)INT_MAX_;
-  uint4 out;
-  out.x = __shfl_sync(FULL, mine, 0);
-  out.y = __shfl_sync(FULL, mine, 8);
-  out.z = __shfl_sync(FULL, mine, 16);
-  out.w = __shfl_sync(FULL, mine, 24);
-  return out;
-}
-
-template <typename T, int W>
-__device__ __noinline__ uint4 bilinear_err4_ni(const Search<T> &S, int tr, int tc, int hstep, unsigned validmask) {
-  return bilinear_err4_body<T, W>(S, tr, tc, hstep, validmask);
-}
-template <typename T, int W>
-__device__ __forceinline__ uint4 bilinear_err4(const Search<T> &S, int tr, int tc, int hstep, unsigned validmask) {
-  if constexpr (InlineSubpel<W>::value) return bilinear_err4_body<T, W>(S, tr, tc, hstep, validmask);
-  else return bilinear_err4_ni<T, W>(S, tr, tc, hstep, validmask);
-}
-
 // ---------------------------------------------------------------------------
 // Sub-pel error out of shared memory only.  subpel_search() makes sure the search window covers every
 // candidate of the sub-pel stage (all lie within two full-pel steps of its start) and the source block is
@@ -1155,16 +1003,13 @@ __device__ __forceinline__ uint4 bilinear_err4(const Search<T> &S, int tr, int t
 //   sum(d) = sum(d') - 4096 n,   sum(d^2) = sum(d'^2) - 8192 sum(d') + n 2^24   (exact; evaluated mod 2^32,
 // the true per-lane value is below 2^32).
 // ---------------------------------------------------------------------------
-#ifndef TF_SUBPEL_WIN
-#define TF_SUBPEL_WIN 1
-#endif
 template <typename T, int W>
 __device__ __forceinline__ unsigned win_origin(const Search<T> &S) {  // shared address of MV (0, 0), row 0
   return (unsigned)__cvta_generic_to_shared(S.win) +
          (unsigned)((S.wR - S.wr) * WinCfg<T, W>::PITCH + (S.wR - S.wc) * (int)sizeof(T) + S.wshift);
 }
 template <typename T, int W>
-__device__ __forceinline__ unsigned subpel_err_win_body(const Search<T> &S_in, int r8, int c8, int mode) {
+__device__ __forceinline__ unsigned subpel_err_win(const Search<T> &S_in, int r8, int c8, int mode) {
   const Search<T> S = S_in;
   const int lane = lane_id();
   const int fr = r8 >> 3, fc = c8 >> 3;
@@ -1225,19 +1070,14 @@ __device__ __forceinline__ unsigned subpel_err_win_body(const Search<T> &S_in, i
   unsigned sse_out;
   return var_finish(sum, sse64, W, S.hbd_shift, &sse_out);
 }
+// The four first-level candidates of a sub-pel round (left, right, up, down of (tr, tc) at distance hstep;
+// first_level_check, mcomp.c:2503-2541) evaluated in one pass: their errors do not depend on the incumbent, so the
+// reference's sequential comparisons can be replayed on the four results afterwards.  Lane group g = lane / 8
+// evaluates candidate g; a lane owns one (W = 16) or two (W = 32) column pairs over all rows, so there is no band
+// overhead and one reduction / variance epilogue serves all four.  Candidates whose bit in validmask is clear are
+// not read (their group re-reads the centre) and return INT_MAX.
 template <typename T, int W>
-__device__ __noinline__ unsigned subpel_err_win_ni(const Search<T> &S, int r8, int c8, int mode) {
-  return subpel_err_win_body<T, W>(S, r8, c8, mode);
-}
-template <typename T, int W>
-__device__ __forceinline__ unsigned subpel_err_win(const Search<T> &S, int r8, int c8, int mode) {
-  if constexpr (InlineSubpel<W>::value) return subpel_err_win_body<T, W>(S, r8, c8, mode);
-  else return subpel_err_win_ni<T, W>(S, r8, c8, mode);
-}
-
-// The batched first-level pass (see bilinear_err4) out of shared memory only.
-template <typename T, int W>
-__device__ __forceinline__ uint4 subpel_err4_win_body(const Search<T> &S_in, int tr, int tc, int hstep, unsigned validmask) {
+__device__ __forceinline__ uint4 subpel_err4_win(const Search<T> &S_in, int tr, int tc, int hstep, unsigned validmask) {
   const Search<T> S = S_in;
   constexpr int ES = (int)sizeof(T);
   constexpr int WP = WinCfg<T, W>::PITCH, SP = SrcTile<T, W>::PITCH;
@@ -1323,16 +1163,6 @@ __device__ __forceinline__ uint4 subpel_err4_win_body(const Search<T> &S_in, int
   out.w = __shfl_sync(FULL, mine, 24);
   return out;
 }
-template <typename T, int W>
-__device__ __noinline__ uint4 subpel_err4_win_ni(const Search<T> &S, int tr, int tc, int hstep, unsigned validmask) {
-  return subpel_err4_win_body<T, W>(S, tr, tc, hstep, validmask);
-}
-template <typename T, int W>
-__device__ __forceinline__ uint4 subpel_err4_win(const Search<T> &S, int tr, int tc, int hstep, unsigned validmask) {
-  if constexpr (InlineSubpel<W>::value) return subpel_err4_win_body<T, W>(S, tr, tc, hstep, validmask);
-  else return subpel_err4_win_ni<T, W>(S, tr, tc, hstep, validmask);
-}
-
 __device__ __forceinline__ int clip_px(int v, int bd) {
   const int m = (1 << bd) - 1;
   return v < 0 ? 0 : (v > m ? m : v);
@@ -1409,8 +1239,7 @@ struct Subpel {
 template <typename T, int W>
 __device__ __forceinline__ unsigned check_better(Subpel<T, W> &sp, int r8, int c8, bool accurate, int *is_better) {
   if (!in_range(sp.lim, r8, c8)) return (unsigned)INT_MAX_;
-  const unsigned cost = accurate ? upsampled_err<T, W>(*sp.S, r8, c8, sp.bd, sp.tmp)
-                                 : (TF_SUBPEL_WIN ? subpel_err_win<T, W>(*sp.S, r8, c8, 1) : bilinear_err<T, W>(*sp.S, r8, c8));
+  const unsigned cost = accurate ? upsampled_err<T, W>(*sp.S, r8, c8, sp.bd, sp.tmp) : subpel_err_win<T, W>(*sp.S, r8, c8, 1);
   if (cost < sp.besterr) {
     sp.besterr = cost;
     sp.best.row = r8;
@@ -1424,9 +1253,9 @@ __device__ __forceinline__ unsigned check_better(Subpel<T, W> &sp, int r8, int c
 template <typename T, int W>
 __device__ MV2 first_level(Subpel<T, W> &sp, MV2 t, int hstep, bool accurate) {
   unsigned left, right, up, down;
-  // The batched pass pays off for the throughput-bound 16x16 searches; the latency-bound 32x32 search
-  // is faster with four short passes than with one pass of four times the dependent work per lane.
-  if (accurate || (W == 32 && !TF_S32_ERR4)) {
+  // (Round 1 kept four short passes for the 32x32 search; with the routines inlined and reading shared memory
+  // only, the batched pass is faster there too: 60.4 -> 61.5 frames/s at 4K 10-bit.)
+  if (accurate) {
     left = check_better(sp, t.row, t.col - hstep, accurate, nullptr);
     right = check_better(sp, t.row, t.col + hstep, accurate, nullptr);
     up = check_better(sp, t.row - hstep, t.col, accurate, nullptr);
@@ -1435,7 +1264,7 @@ __device__ MV2 first_level(Subpel<T, W> &sp, MV2 t, int hstep, bool accurate) {
     // one pass for the four candidates, then check_better's comparisons in the reference's order
     const unsigned vm = (in_range(sp.lim, t.row, t.col - hstep) ? 1u : 0u) | (in_range(sp.lim, t.row, t.col + hstep) ? 2u : 0u) |
                         (in_range(sp.lim, t.row - hstep, t.col) ? 4u : 0u) | (in_range(sp.lim, t.row + hstep, t.col) ? 8u : 0u);
-    const uint4 c = TF_SUBPEL_WIN ? subpel_err4_win<T, W>(*sp.S, t.row, t.col, hstep, vm) : bilinear_err4<T, W>(*sp.S, t.row, t.col, hstep, vm);
+    const uint4 c = subpel_err4_win<T, W>(*sp.S, t.row, t.col, hstep, vm);
     left = c.x, right = c.y, up = c.z, down = c.w;
     const int dr[4] = { 0, 0, -hstep, hstep }, dc[4] = { -hstep, hstep, 0, 0 };
     const unsigned cs[4] = { left, right, up, down };
@@ -1490,7 +1319,7 @@ __device__ void second_level_v2(Subpel<T, W> &sp, MV2 t, MV2 diag) {
 // av1_find_best_sub_pixel_tree{,_pruned,_pruned_more} (mcomp.c:2844-3133) with
 // cost_list == NULL, forced_stop = EIGHTH_PEL, MV_COST_NONE, unscaled refs.
 template <typename T, int W>
-__device__ __forceinline__ unsigned subpel_search_body(Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
+__device__ __forceinline__ unsigned subpel_search(Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
   Subpel<T, W> sp;
   sp.S = &S;
   sp.bd = P.is_hbd ? P.bit_depth : 8;
@@ -1515,18 +1344,10 @@ __device__ __forceinline__ unsigned subpel_search_body(Search<T> &S, const KPara
     }
   } else {
     // every candidate of the stage lies within two full-pel steps of its start: one window for all of them
-    if (TF_SUBPEL_WIN && !window_covers(S, start_full.row, start_full.col, 2))
+    if (!window_covers(S, start_full.row, start_full.col, 2))
       window_load<T, W>(S, reinterpret_cast<unsigned char *>(tmp), start_full.row, start_full.col);
     // setup_center_error (mcomp.c:2718-2777): vf(ref, src); the variance is symmetric in its arguments
-    if constexpr (TF_SUBPEL_WIN != 0) {
-      sp.besterr = subpel_err_win<T, W>(S, start.row, start.col, 2);
-    } else if constexpr (VAR_VIA_SUBPEL_ROUTINE) {
-      sp.besterr = bilinear_err<T, W>(S, start.row, start.col, 2);
-    } else {
-      unsigned sse;
-      sp.besterr = variance<T, W>(S.ref + start_full.row * S.stride + start_full.col, S.stride, S.src, S.stride,
-                                  S.hbd_shift, &sse);
-    }
+    sp.besterr = subpel_err_win<T, W>(S, start.row, start.col, 2);
     const int rounds = P.allow_hp ? 3 : 2;
     for (int it = 0; it < rounds; it++) {
       const MV2 center = sp.best;
@@ -1537,16 +1358,6 @@ __device__ __forceinline__ unsigned subpel_search_body(Search<T> &S, const KPara
   }
   *best = sp.best;
   return sp.besterr;
-}
-
-template <typename T, int W>
-__device__ __noinline__ unsigned subpel_search_ni(Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
-  return subpel_search_body<T, W>(S, P, start_full, best, tmp);
-}
-template <typename T, int W>
-__device__ __forceinline__ unsigned subpel_search(Search<T> &S, const KParams &P, MV2 start_full, MV2 *best, T *tmp) {
-  if constexpr (InlineSubpel<W>::value) return subpel_search_body<T, W>(S, P, start_full, best, tmp);
-  else return subpel_search_ni<T, W>(S, P, start_full, best, tmp);
 }
 
 __device__ __forceinline__ int rawpel(int x) { return (x + 3 + (x >= 0)) >> 3; }  // GET_MV_RAWPEL mv.h:28

@@ -1,3 +1,5 @@
+# A/B of builds on one box: the GPU suite on the in-tree build, then every gpurun_ab/lib_*.so (built with different -D switches)
+# on three workloads (TF_GPU_LIB selects the library).  usage (via gpurun): bash scripts/gpu_ab_sweep.sh
 cd $GRAFT_REPO_ROOT
 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log | cut -c1-300
 run() { wl=$1; f=$2; shift 2
