@@ -9,6 +9,7 @@
 // frame and FRAME_DIFF.  No CPU fallback: without a CUDA device every entry
 // point returns TF_GPU_ERR_NO_DEVICE.
 #include "tf_kernels.cuh"
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no libcuda link)
 
 #include <math.h>
 #include <stdarg.h>
@@ -44,6 +45,9 @@ struct DevFrame {
   void *base[3] = { nullptr, nullptr, nullptr };  // allocation base
   void *p00[3] = { nullptr, nullptr, nullptr };   // pixel (0,0)
   cudaEvent_t ready = nullptr;                    // upload + border extension finished (copy stream)
+  // TMA descriptors of the luma plane (device memory, 2 x 128 bytes: box of a 16x16 and of a 32x32 skip-row
+  // candidate), see make_tensor_maps(); nullptr when the driver has no tensor-map encoder
+  void *d_tmap = nullptr;
 };
 
 // Timing events of one filter call (main stream): start, after the search32 chain, after the
@@ -183,7 +187,50 @@ bool make_geometry(const tf_gpu_frame *f, int num_planes, Geometry *g, int luma_
   return true;
 }
 
-int alloc_dev_frame(tf_gpu_ctx *ctx, DevFrame *d, const Geometry &g) {
+// TMA descriptors for the far candidates of the search kernels: the luma allocation as a 3-D tensor
+// (x, row parity, row / 2) so that a box of (W + pad, 1, W / 2) elements at (X & ~(pad - 1), Y & 1, Y >> 1) holds
+// exactly the W / 2 rows Y, Y + 2, ... of a skip-row SAD candidate (aom_dsp/sad.c:66-70), landing dense in
+// shared memory (pad = 16 bytes of samples: the innermost box coordinate has to be 16-byte aligned).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+int make_tensor_maps(tf_gpu_ctx *ctx, DevFrame *d) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(ctx, TF_GPU_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+  const Geometry &g = d->g;
+  const size_t es = g.is_hbd ? 2 : 1;
+  alignas(64) CUtensorMap maps[2];
+  for (int k = 0; k < 2; k++) {
+    const cuuint32_t W = k ? 32 : 16;
+    const cuuint64_t dims[3] = { (cuuint64_t)g.pitch[0], 2, (cuuint64_t)(g.rows[0] / 2) };
+    const cuuint64_t strides[2] = { (cuuint64_t)g.pitch[0] * es, (cuuint64_t)g.pitch[0] * es * 2 };
+    // the innermost start coordinate of a box copy must be 16-byte aligned (an unaligned one is an illegal
+    // instruction): the box is 16 bytes wider than the candidate and starts at the aligned column below it
+    const cuuint32_t box[3] = { W + (cuuint32_t)(16 / es), 1, W / 2 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    const CUresult r = enc(&maps[k], g.is_hbd ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, d->base[0], dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, TF_GPU_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
+  if (!d->d_tmap) CU(cudaMalloc(&d->d_tmap, sizeof(maps)));
+  CU(cudaMemcpy(d->d_tmap, maps, sizeof(maps), cudaMemcpyHostToDevice));
+  return TF_GPU_OK;
+}
+
+int alloc_dev_frame(tf_gpu_ctx *ctx, DevFrame *d, const Geometry &g, bool with_maps = false) {
   const size_t es = g.is_hbd ? 2 : 1;
   if (d->base[0] && d->g == g) return TF_GPU_OK;
   for (int p = 0; p < 3; p++) {
@@ -198,6 +245,7 @@ int alloc_dev_frame(tf_gpu_ctx *ctx, DevFrame *d, const Geometry &g) {
     CU(cudaMalloc(&d->base[p], bytes));
     d->p00[p] = (char *)d->base[p] + ((size_t)g.by[k] * g.pitch[k] + g.bx[k]) * es;
   }
+  if (with_maps && TF_FAR_TMA) return make_tensor_maps(ctx, d);  // descriptors only for the build that uses them
   return TF_GPU_OK;
 }
 
@@ -266,7 +314,7 @@ int get_frame(tf_gpu_ctx *ctx, const tf_gpu_frame *f, int num_planes, DevFrame *
       }
     }
     if (!victim) return fail(ctx, TF_GPU_ERR_MEM, "frame cache too small for this window");
-    int rc = alloc_dev_frame(ctx, victim, g);
+    int rc = alloc_dev_frame(ctx, victim, g, true);
     if (rc) return rc;
     victim->valid = false;
     {
@@ -407,6 +455,8 @@ void fill_kparams(const tf_gpu_ctx *ctx, const tf_gpu_params *p, const Geometry 
     K.pitch[k] = g.pitch[k];
     K.out_pitch[k] = ctx->out.g.pitch[k];
   }
+  K.abx = g.bx[0];
+  K.aby = g.by[0];
   K.border = p->border_in_pixels;
   K.num_frames = p->num_frames;
   K.filter_idx = p->filter_frame_idx;
@@ -461,8 +511,10 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     double thr = min_frame_size * 0.1;  // TF_SEARCH_DISTANCE_THRESHOLD, :603-604
     K.dist_thr = thr > 1 ? thr : 1;
   }
-  for (int f = 0; f < p->num_frames; f++)
+  for (int f = 0; f < p->num_frames; f++) {
     for (int pl = 0; pl < p->num_planes; pl++) K.frm[f][pl] = frames[f]->p00[pl];
+    K.tmap[f] = frames[f]->d_tmap;
+  }
   for (int pl = 0; pl < p->num_planes; pl++) {
     K.out[pl] = ctx->out.p00[pl];
     if (ctx->peer_out[pl]) {  // the owner rank's plane: same geometry, hence the same pitch
@@ -539,10 +591,10 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
     Kf.frame_end = p->num_frames;
     const bool dense = grid > ctx->num_sms * S32_WARPS_LO;  // resident at once only with the denser build
     if (g.is_hbd) {
-      if (dense) tf_search32_kernel<uint16_t, S32_WARPS_HI_HBD><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
+      if (dense) tf_search32_kernel<uint16_t, S32_WARPS_HI_HBD><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL_BASE, ctx->stream>>>(Kf);
       else tf_search32_kernel<uint16_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
     } else {
-      if (dense) tf_search32_kernel<uint8_t, S32_WARPS_HI><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
+      if (dense) tf_search32_kernel<uint8_t, S32_WARPS_HI><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL_BASE, ctx->stream>>>(Kf);
       else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
     }
     nlaunch++;
@@ -572,10 +624,10 @@ int launch_filter(tf_gpu_ctx *ctx, const tf_gpu_params *p, DevFrame *const *fram
       const int hi = g.is_hbd ? S32_WARPS_HI_HBD : S32_WARPS_HI;
       const bool one_wave = grid <= ctx->num_sms * hi && grid > ctx->num_sms * S32_WARPS_LO;
       if (g.is_hbd) {
-        if (one_wave) tf_search32_kernel<uint16_t, S32_WARPS_HI_HBD><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
+        if (one_wave) tf_search32_kernel<uint16_t, S32_WARPS_HI_HBD><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL_BASE, ctx->stream>>>(Kf);
         else tf_search32_kernel<uint16_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(Kf);
       } else {
-        if (one_wave) tf_search32_kernel<uint8_t, S32_WARPS_HI><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
+        if (one_wave) tf_search32_kernel<uint8_t, S32_WARPS_HI><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL_BASE, ctx->stream>>>(Kf);
         else tf_search32_kernel<uint8_t, S32_WARPS_LO><<<grid, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(Kf);
       }
       nlaunch++;
@@ -886,6 +938,7 @@ void tf_gpu_destroy(tf_gpu_ctx *ctx) {
   for (auto &d : ctx->cache) {
     for (int p = 0; p < 3; p++)
       if (d.base[p]) cudaFree(d.base[p]);
+    if (d.d_tmap) cudaFree(d.d_tmap);
     if (d.ready) cudaEventDestroy(d.ready);
   }
   for (int i = 0; i < 2; i++)
@@ -1226,6 +1279,7 @@ int tf_gpu_fullpel_search_batch(tf_gpu_ctx *ctx, const tf_gpu_params *params, co
   }
   KParams K;
   fill_kparams(ctx, &p, g, K);
+  K.tmap[1] = dr->d_tmap;  // the reference frame's TMA descriptors (the kernel searches frame pair (0, 1))
   rc = ensure_dump(ctx, 10, (size_t)n * sizeof(SearchItem));
   if (rc) return rc;
   rc = ensure_dump(ctx, 11, (size_t)n * sizeof(SearchResult));
@@ -1237,12 +1291,12 @@ int tf_gpu_fullpel_search_batch(tf_gpu_ctx *ctx, const tf_gpu_params *params, co
   CU(cudaStreamWaitEvent(ctx->stream, dr->ready, 0));
   if (g.is_hbd) {
     const uint16_t *a = (const uint16_t *)ds->p00[0], *b = (const uint16_t *)dr->p00[0];
-    if (block_size == 32) tf_fullpel_batch_kernel<uint16_t, 32><<<n, 32, WIN_BYTES, ctx->stream>>>(K, a, b, d_items, d_res, n);
-    else tf_fullpel_batch_kernel<uint16_t, 16><<<n, 32, WIN16_BYTES, ctx->stream>>>(K, a, b, d_items, d_res, n);
+    if (block_size == 32) tf_fullpel_batch_kernel<uint16_t, 32><<<n, 32, SearchSmem<uint16_t, 32>::TOTAL, ctx->stream>>>(K, a, b, d_items, d_res, n);
+    else tf_fullpel_batch_kernel<uint16_t, 16><<<n, 32, SearchSmem<uint16_t, 16>::TOTAL, ctx->stream>>>(K, a, b, d_items, d_res, n);
   } else {
     const uint8_t *a = (const uint8_t *)ds->p00[0], *b = (const uint8_t *)dr->p00[0];
-    if (block_size == 32) tf_fullpel_batch_kernel<uint8_t, 32><<<n, 32, WIN_BYTES, ctx->stream>>>(K, a, b, d_items, d_res, n);
-    else tf_fullpel_batch_kernel<uint8_t, 16><<<n, 32, WIN16_BYTES, ctx->stream>>>(K, a, b, d_items, d_res, n);
+    if (block_size == 32) tf_fullpel_batch_kernel<uint8_t, 32><<<n, 32, SearchSmem<uint8_t, 32>::TOTAL, ctx->stream>>>(K, a, b, d_items, d_res, n);
+    else tf_fullpel_batch_kernel<uint8_t, 16><<<n, 32, SearchSmem<uint8_t, 16>::TOTAL, ctx->stream>>>(K, a, b, d_items, d_res, n);
   }
   CU(cudaGetLastError());
   ctx->last_launches++;

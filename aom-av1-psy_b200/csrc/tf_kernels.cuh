@@ -73,6 +73,8 @@ struct KParams {
   // planes (pointers to pixel (0,0)); pitch in samples
   const void *frm[MAXF][3];
   int pitch[2];
+  const void *tmap[MAXF];  // per frame: TMA descriptors of the luma plane (16x16 box, then 32x32 box), device memory
+  int abx, aby;             // position of pixel (0, 0) inside the luma allocation the descriptors describe
   void *out[3];
   int out_pitch[2];
   unsigned long long *diff;  // [2]
@@ -152,6 +154,11 @@ struct Search {
   // from global memory through L1.
   unsigned char *win;  // nullptr = no window
   unsigned srcs;       // shared address of the source-block tile (SrcTile layout), 0 = not staged
+  // TMA staging of far candidates (diamond_search): the block's origin in allocation coordinates, the reference
+  // frame's descriptor for this block size, the staging buffer and its mbarrier (shared addresses)
+  int ax, ay;
+  const void *tmap;
+  unsigned farbuf, mbar;
   int wr, wc, wR;
   int wpitch;  // bytes; wpitch/4 is odd
   int wshift;  // bytes the window origin was aligned down by
@@ -198,10 +205,31 @@ struct SrcTile {
   static constexpr int BYTES = W * PITCH;
 };
 // Dynamic shared memory of a search kernel: the window, then the source tile.
+// TF_FAR_TMA: far candidates of a diamond stage staged through TMA (cp.async.bulk.tensor, UTMALDG) instead of
+// per-lane global loads.  Built, parity-green (the whole GPU suite passes with it) and measured on one box against
+// the default: 4K 10-bit 54.8 vs 62.6 frames/s, 1080p 10-bit 318 vs 330, 1080p 8-bit 476 vs 499 -- the copies of a
+// stage are issued by one lane (as many issue slots as the loads they replace), their round trip is longer than
+// an L2 load's and nothing of the warp overlaps it, and because the innermost box coordinate must be 16-byte
+// aligned (an unaligned start is an illegal instruction: scripts/tma_probe.cu) the candidates do not land aligned,
+// so the funnel shifts stay.  Off by default; -DTF_FAR_TMA=1 builds it.
+#ifndef TF_FAR_TMA
+#define TF_FAR_TMA 0
+#endif
 template <typename T, int W>
 struct SearchSmem {
   static constexpr int WIN = (WinCfg<T, W>::ROWS * WinCfg<T, W>::PITCH + 15) / 16 * 16;
-  static constexpr int TOTAL = WIN + SrcTile<T, W>::BYTES;
+  static constexpr int TOTAL_BASE = WIN + SrcTile<T, W>::BYTES;  // kernels without the TMA staging buffer
+  // far candidates of a diamond stage land here through TMA: the W/2 even rows of a candidate (skip-row SAD), each
+  // row from the 16-byte aligned column at or below the candidate's; eight sites of a stage at a time for the
+  // 16x16 search, four for the 32x32 search
+  static constexpr int FAR_PAD = 16 / (int)sizeof(T);                  // samples: the box starts at the 16-byte aligned column
+  static constexpr int FAR_ROWB = (W + FAR_PAD) * (int)sizeof(T);       // bytes per staged row
+  static constexpr int FAR_CAND = FAR_ROWB * (W / 2);                   // a multiple of 128 for every (T, W)
+  static constexpr int FAR_SLOTS = W == 16 ? 8 : 4;
+  static_assert(FAR_CAND % 128 == 0, "TMA destinations are 128-byte aligned");
+  static constexpr int FAR = (TOTAL_BASE + 127) / 128 * 128;
+  static constexpr int MBAR = FAR + FAR_SLOTS * FAR_CAND;  // 8-byte mbarrier, then its phase word
+  static constexpr int TOTAL = TF_FAR_TMA ? MBAR + 16 : TOTAL_BASE;
   static_assert((W + 7) * W * (int)sizeof(T) <= WIN, "8-tap scratch of SUBPEL_TREE lives in the window buffer");
 };
 template <typename T, int W>
@@ -350,6 +378,50 @@ __device__ __forceinline__ uint32_t lds_u16(unsigned addr) {
   asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+// mbarrier + TMA (cp.async.bulk.tensor) wrappers for the far-candidate staging; shared addresses are 32-bit.
+__device__ __forceinline__ void sts_u32(unsigned addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  // bounded: a copy that never completes (a descriptor / coordinate bug) traps instead of hanging the GPU
+  for (unsigned spin = 0;; spin++) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const void *tmap, int c0, int c1, int c2, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+               : "memory");
+}
+// Staging set-up of a search kernel: one mbarrier per warp-CTA, phase word next to it.
+template <typename T, int W>
+__device__ __forceinline__ void far_stage_init(Search<T> &S, unsigned char *smem_raw, int ax, int ay) {
+  S.ax = ax;
+  S.ay = ay;
+  S.farbuf = (unsigned)__cvta_generic_to_shared(smem_raw + SearchSmem<T, W>::FAR);
+  S.mbar = (unsigned)__cvta_generic_to_shared(smem_raw + SearchSmem<T, W>::MBAR);
+  if (lane_id() == 0) {
+    mbar_init(S.mbar, 1);
+    sts_u32(S.mbar + 8, 0);
+  }
+  __syncwarp();
+}
 template <typename T, int W, bool SKIP>
 __device__ __forceinline__ unsigned sad_partial_win(unsigned win_origin /* shared addr of MV (0,0), row 0 */,
                                                     int wpitch, int r, int c, int row,
@@ -485,6 +557,31 @@ __device__ __forceinline__ unsigned far_partial_off(const unsigned char *lane_ba
   return s;
 }
 
+// SAD of a staged candidate against the source block in the far (row-major) lane layout; dxb = byte offset of
+// the candidate's first sample inside a staged row (0 .. 15).
+template <typename T, int W, bool SKIP>
+__device__ __forceinline__ unsigned far_partial_smem(unsigned cand, int dxb, int lane, const uint32_t (&sf)[FarL<T, W, SKIP>::IT]) {
+  using F = FarL<T, W, SKIP>;
+  constexpr int ROWB = SearchSmem<T, W>::FAR_ROWB;
+  const unsigned a = cand + (unsigned)((lane / F::NW) * ROWB + (lane % F::NW) * 4 + (dxb & ~3));
+  const unsigned sh = (unsigned)(dxb & 3) * 8;
+  uint32_t w0[F::IT], w1[F::IT];
+#pragma unroll
+  for (int it = 0; it < F::IT; it++) {
+    w0[it] = lds_u32(a + (unsigned)(it * F::RPI * ROWB));
+    w1[it] = lds_u32(a + (unsigned)(it * F::RPI * ROWB + 4));
+  }
+  unsigned s = 0;
+#pragma unroll
+  for (int it = 0; it < F::IT; it++) {
+    const unsigned x = __funnelshift_r(w0[it], w1[it], sh);
+    if (sizeof(T) == 1) s = __vsadu4(x, sf[it]) + s;
+    else s += __vmaxu2(x, sf[it]) - __vminu2(x, sf[it]);
+  }
+  if (sizeof(T) != 1) s = (s & 0xffffu) + (s >> 16);
+  return s;
+}
+
 // ---------------------------------------------------------------------------
 // Variance (aom_dsp/variance.c:56-72,141-148; hbd :342-429).  a - b, W x W.
 // Lane = column (W == 32) or (row half, column) (W == 16).
@@ -554,7 +651,7 @@ __device__ __forceinline__ int var_cost(const Search<T> &S, int r, int c) {
 // over keys (total << 4 | site index): bit-exact, and without any sequential
 // per-candidate code.
 // ---------------------------------------------------------------------------
-template <typename T, int W, bool SKIP>
+template <typename T, int W, bool SKIP, bool TMAF>
 __device__ __forceinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start, int search_step, int *num00,
                                                 MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
@@ -643,6 +740,63 @@ __device__ __forceinline__ unsigned diamond_search(const Search<T> &S_in, MV2 st
       // incumbent of a predicted start, few candidates die early, and the second dependent load round trip
       // lengthens the chain: 45.9 vs 51.0 frames/s.)
       ncand += __popc(okmask);
+      if constexpr (SKIP && TMAF) {
+        // TMA staging: one lane issues a box copy per live site (the descriptor views the plane as (x, row
+        // parity, row / 2), so a box of one parity is the candidate's even rows; it starts at the 16-byte aligned
+        // column at or below the candidate's, the only start the copy engine accepts); the copies of a batch are
+        // all in flight before anything is evaluated, bypass the L1 load path the per-lane global loads of this
+        // stage saturate, and complete on the warp's mbarrier.
+        using SM = SearchSmem<T, W>;
+        const int cx = S.ax + sc, cy = S.ay + sr;  // the candidate's first sample in allocation coordinates
+        unsigned phase = lds_u32(S.mbar + 8);
+#pragma unroll 1
+        for (unsigned m = okmask; m != 0;) {
+          unsigned batch = 0;
+          int nb = 0;
+#pragma unroll 1
+          for (; m != 0 && nb < SM::FAR_SLOTS; nb++) {
+            batch |= m & (0u - m);
+            m &= m - 1;
+          }
+          if (lane == 0) mbar_expect_tx(S.mbar, (unsigned)(nb * SM::FAR_CAND));
+          {
+            unsigned dst = S.farbuf;
+#pragma unroll 1
+            for (unsigned b = batch; b != 0; b &= b - 1, dst += SM::FAR_CAND) {
+              const int i = __ffs(b) - 1;
+              const int x = __shfl_sync(FULL, cx, i), y = __shfl_sync(FULL, cy, i);
+              if (lane == 0) tma_load_3d(dst, S.tmap, x & ~(SM::FAR_PAD - 1), y & 1, y >> 1, S.mbar);
+            }
+          }
+          mbar_wait(S.mbar, phase);
+          phase ^= 1u;
+          unsigned cand = S.farbuf;
+#pragma unroll 1
+          for (unsigned b = batch; b != 0;) {
+            int si[4];
+            unsigned part[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              si[u] = b ? __ffs(b) - 1 : -1;
+              b &= b - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int dxb = (__shfl_sync(FULL, cx, si[u] & 31) & (SM::FAR_PAD - 1)) * (int)sizeof(T);
+              part[u] = si[u] >= 0 ? far_partial_smem<T, W, SKIP>(cand + (unsigned)(u * SM::FAR_CAND), dxb, lane, sf) : 0u;
+            }
+            cand += 4 * SM::FAR_CAND;
+            const unsigned tot4 = reduce4_u32(part, lane);
+            const int ms = (lane & 16) ? ((lane & 8) ? si[3] : si[2]) : ((lane & 8) ? si[1] : si[0]);
+            const unsigned my_cost = __shfl_sync(FULL, scost, ms & 31);
+            const unsigned tot = sad_post<SKIP>(tot4, S.hbd_shift) + my_cost;
+            mykey = min(mykey, ms >= 0 ? ((tot << 4) | (unsigned)(ms + 1)) : 0xffffffffu);
+          }
+          __syncwarp();  // every lane has read the batch before the next one overwrites the buffer
+        }
+        if (lane == 0) sts_u32(S.mbar + 8, phase);
+        __syncwarp();
+      } else
 #pragma unroll 1
       for (int i0 = 0; i0 < nsites; i0 += 4) {
         if (((okmask >> i0) & 15u) == 0) continue;
@@ -689,7 +843,7 @@ __device__ __forceinline__ unsigned diamond_search(const Search<T> &S_in, MV2 st
 }
 
 // full_pixel_diamond (mcomp.c:1421-1470), cost_list == NULL
-template <typename T, int W, bool SKIP>
+template <typename T, int W, bool SKIP, bool TMAF>
 __device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param, MV2 *best_mv) {
   int n = 0, num00 = 0;
   int bestsme = 0;
@@ -708,7 +862,7 @@ __device__ int full_pixel_diamond(const Search<T> &S, MV2 start, int step_param,
     }
     MV2 tmp;
     int nn;
-    int thissme = (int)diamond_search<T, W, SKIP>(S, start, step_param + (first ? 0 : n), &nn, &tmp);
+    int thissme = (int)diamond_search<T, W, SKIP, TMAF>(S, start, step_param + (first ? 0 : n), &nn, &tmp);
     if (thissme < INT_MAX_) {
       // var_cost is a pure function of the MV: passes that end on an MV already scored reuse the value
       if (!first && tmp.row == best_mv->row && tmp.col == best_mv->col) thissme = bestsme;
@@ -843,11 +997,11 @@ __device__ int full_pixel_exhaustive(Search<T> &S, const KParams &P, MV2 start, 
 // av1_full_pixel_search (mcomp.c:1693-1832), NSTEP, run_mesh_search = 1.
 // Returns 1 when the skip-row result must be discarded and the search redone
 // with full SAD (mcomp.c:1777-1810).
-template <typename T, int W, bool SKIP>
+template <typename T, int W, bool SKIP, bool TMAF>
 __device__ __forceinline__ int full_pixel_search_pass(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv,
                                                    unsigned char *winbuf) {
   int run_mesh = 1;
-  int var = full_pixel_diamond<T, W, SKIP>(S, start, P.step_param, best_mv);
+  int var = full_pixel_diamond<T, W, SKIP, TMAF>(S, start, P.step_param, best_mv);
   int prune = 0, thr = 4;
   if (P.prune_level == 2) prune = 1;
   if (P.prune_level == 1) {
@@ -887,7 +1041,7 @@ __device__ __forceinline__ int full_pixel_search_pass(Search<T> &S, const KParam
   return 0;
 }
 
-template <typename T, int W>
+template <typename T, int W, bool TMAF>
 __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2 *best_mv, unsigned char *winbuf) {
   const int wr = iclamp(start.row, S.lim.row_min, S.lim.row_max);
   const int wc = iclamp(start.col, S.lim.col_min, S.lim.col_max);
@@ -896,13 +1050,13 @@ __device__ void full_pixel_search(Search<T> &S, const KParams &P, MV2 start, MV2
   // best_mv, normally inside the window); SUBPEL_TREE reuses the buffer as 8-tap scratch instead.
   const bool keep = P.subpel_method != 0;
   if (P.use_skip) {
-    if (!full_pixel_search_pass<T, W, true>(S, P, start, best_mv, winbuf)) {
+    if (!full_pixel_search_pass<T, W, true, TMAF>(S, P, start, best_mv, winbuf)) {
       if (!keep) S.win = nullptr;
       return;
     }
     if (S.wr != wr || S.wc != wc) window_load<T, W>(S, winbuf, wr, wc);
   }
-  full_pixel_search_pass<T, W, false>(S, P, start, best_mv, winbuf);
+  full_pixel_search_pass<T, W, false, false>(S, P, start, best_mv, winbuf);
   if (!keep) S.win = nullptr;
 }
 
@@ -1378,6 +1532,9 @@ __device__ __forceinline__ void search_init(Search<T> &S, const KParams &P, int 
   S.is_hbd = P.is_hbd;
   S.win = nullptr;
   S.srcs = 0;
+  S.ax = S.ay = 0;
+  S.tmap = nullptr;
+  S.farbuf = S.mbar = 0;
   S.wr = S.wc = S.wR = S.wpitch = S.wshift = 0;
   S.ctr = P.ctr;
   // av1_set_mv_{row,col}_limits (mcomp.h:216-240) + av1_set_mv_search_range (mcomp.c:196-215)
@@ -1414,7 +1571,7 @@ constexpr int S32_WARPS_HI = TF_S32_HI, S32_WARPS_HI_HBD = TF_S32_HI_HBD, S32_WA
 constexpr int S16_WARPS = TF_S16_WARPS;
 template <typename T, int MINB>
 __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
   const int mb_row = P.row_begin + blockIdx.x / P.mb_cols;
   const int mb_col = blockIdx.x % P.mb_cols;
@@ -1426,6 +1583,8 @@ __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_cons
   search_init(S, P, mb_row, mb_col);
   S.src = cur + y_offset;
   src_tile_load<T, 32>(S, smem_raw + SearchSmem<T, 32>::WIN);  // once per block: the same source for every frame
+  constexpr bool TMAF = TF_FAR_TMA && MINB == S32_WARPS_LO;  // the denser builds have no shared memory to spare
+  if constexpr (TMAF) far_stage_init<T, 32>(S, smem_raw, P.abx + mb_col * 32, P.aby + mb_row * 32);
   // ref_mv chain (temporal_filter.c:855-871): carried in global memory across launches
   MV2 ref_mv = { 0, 0 };
   if (P.frame_begin > 0) {
@@ -1439,9 +1598,10 @@ __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_cons
       continue;
     }
     S.ref = reinterpret_cast<const T *>(P.frm[frame][0]) + y_offset;
+    S.tmap = reinterpret_cast<const unsigned char *>(P.tmap[frame]) + 128;  // the 32x32 box descriptor
     const MV2 start = { rawpel(ref_mv.row), rawpel(ref_mv.col) };
     MV2 best_full;
-    full_pixel_search<T, 32>(S, P, start, &best_full, smem_raw);
+    full_pixel_search<T, 32, TMAF>(S, P, start, &best_full, smem_raw);
     int block_mse;
     MV2 block_mv;
     if (P.force_integer_mv == 1) {
@@ -1479,7 +1639,7 @@ __global__ void __launch_bounds__(32, MINB) tf_search32_kernel(const __grid_cons
 // (:202-205).  One warp per task, frame-major task order for L2 locality.
 template <typename T>
 __global__ void __launch_bounds__(32, S16_WARPS) tf_search16_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
   const int nblk = (P.row_end - P.row_begin) * P.mb_cols;
   const int task = blockIdx.x;
@@ -1499,10 +1659,13 @@ __global__ void __launch_bounds__(32, S16_WARPS) tf_search16_kernel(const __grid
   S.src = reinterpret_cast<const T *>(P.frm[P.filter_idx][0]) + off;
   S.ref = reinterpret_cast<const T *>(P.frm[frame][0]) + off;
   src_tile_load<T, 16>(S, smem_raw + SearchSmem<T, 16>::WIN);
+  if constexpr (TF_FAR_TMA != 0)
+    far_stage_init<T, 16>(S, smem_raw, P.abx + mb_col * 32 + (sub & 1) * 16, P.aby + mb_row * 32 + (sub >> 1) * 16);
+  S.tmap = P.tmap[frame];  // the 16x16 box descriptor
   const size_t bf = (size_t)blk * P.num_frames + frame;
   const MV2 start = { rawpel((int)P.s_blk_mv[bf * 2 + 0]), rawpel((int)P.s_blk_mv[bf * 2 + 1]) };
   MV2 best_full, best;
-  full_pixel_search<T, 16>(S, P, start, &best_full, smem_raw);
+  full_pixel_search<T, 16, TF_FAR_TMA != 0>(S, P, start, &best_full, smem_raw);
   const unsigned err = subpel_search<T, 16>(S, P, best_full, &best, reinterpret_cast<T *>(smem_raw));
   if (lane == 0) {
     P.s_sub_mv[(bf * 4 + sub) * 2 + 0] = (int16_t)best.row;
@@ -1527,7 +1690,7 @@ template <typename T, int W>
 __global__ void __launch_bounds__(32, W == 32 ? S32_WARPS_LO : 24)
     tf_fullpel_batch_kernel(const __grid_constant__ KParams P, const T *src, const T *ref, const SearchItem *items,
                             SearchResult *results, int n) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = lane_id();
   if ((int)blockIdx.x >= n) return;
   const SearchItem it = items[blockIdx.x];
@@ -1545,9 +1708,11 @@ __global__ void __launch_bounds__(32, W == 32 ? S32_WARPS_LO : 24)
   const int off = it.y * P.pitch[0] + it.x;
   S.src = src + off;
   S.ref = ref + off;
+  if constexpr (TF_FAR_TMA != 0) far_stage_init<T, W>(S, smem_raw, P.abx + it.x, P.aby + it.y);
+  S.tmap = reinterpret_cast<const unsigned char *>(P.tmap[1]) + (W == 32 ? 128 : 0);
   const MV2 start = { (int)it.start_row, (int)it.start_col };
   MV2 best;
-  full_pixel_search<T, W>(S, P, start, &best, smem_raw);
+  full_pixel_search<T, W, TF_FAR_TMA != 0>(S, P, start, &best, smem_raw);
   const int var = var_cost<T, W>(S, best.row, best.col);
   if (lane == 0) {
     results[blockIdx.x].row = (int16_t)best.row;
@@ -1931,7 +2096,7 @@ __device__ __forceinline__ WarpSmem carve_smem(unsigned char *raw, int num_pels)
 
 template <typename T>
 __global__ void __launch_bounds__(FILT_THREADS, TF_FILT_MINB) tf_filter_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NT = FILT_THREADS;
   const WarpSmem sm = carve_smem(smem_raw, P.num_pels);
   const int tid = threadIdx.x;
