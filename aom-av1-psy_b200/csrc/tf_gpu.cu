@@ -771,6 +771,8 @@ int submit_impl(tf_gpu_ctx *ctx, const tf_gpu_params *params, const tf_gpu_frame
   const Geometry &g = devf[0]->g;
   rc = validate_geometry(ctx, params, g);
   if (rc) return rc;
+  if (ctx->peer_out[0] || ctx->peer_out[1] || ctx->peer_out[2])
+    return fail(ctx, TF_GPU_ERR_INVALID, "an output plane is imported from another rank: its rows go there, use the resident calls");
   Geometry og = g;
   const bool extend_out = params->extend_output_borders && !(params->out_row_end > params->out_row_begin);
   if (extend_out) {
