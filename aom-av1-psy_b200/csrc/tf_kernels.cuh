@@ -1836,10 +1836,6 @@ __device__ __noinline__ void convolve12(const KParams &P, const T *src, int ss, 
 #ifndef TF_CONVOLVE_PACKED
 #define TF_CONVOLVE_PACKED 1
 #endif
-#ifndef TF_CONV_A_UNROLL
-#define TF_CONV_A_UNROLL 1
-#endif
-constexpr int CONV_A_UNROLL = TF_CONV_A_UNROLL;  // rows of the horizontal stage whose loads are in flight together
 __device__ __forceinline__ unsigned pack_taps(const int16_t *f, int k) {
   return ((unsigned)f[k] & 0xffu) | (((unsigned)f[k + 1] & 0xffu) << 8);
 }
@@ -1868,7 +1864,7 @@ __device__ __noinline__ void convolve12_packed(const KParams &P, const uint16_t 
       const unsigned sh = (a0 & 2) ? 16u : 0u;  // uniform: the pitch and 2 * pc are even
       const unsigned char *row0 = reinterpret_cast<const unsigned char *>(a0 & ~(uintptr_t)3);
       const int off = 1 << (pbd + 6), bits = 7 - r0b;
-#pragma unroll(CONV_A_UNROLL)
+#pragma unroll 1  // (two or three rows in flight: measured, no change)
       for (int y = ry; y < nrows; y += rpi) {
         const uint32_t *wp = reinterpret_cast<const uint32_t *>(row0 + (size_t)y * ss * 2);
         uint32_t wv[8];
