@@ -27,6 +27,10 @@
 namespace tfk {
 
 constexpr unsigned FULL = 0xffffffffu;
+// TF_PU16: near passes of the 16x16 search whose loads are issued back to back (2: 63.5 -> 63.9 frames/s at 4K 10-bit).
+#ifndef TF_PU16
+#define TF_PU16 2
+#endif
 // TF_SAD_IDP: high-bitdepth SAD as sum(a) + sum(b) - 2 sum(min(a, b)) with the sums on the FMA pipe (IDP.2A): the
 // ALU pipe (VIMNMX, shifts, logic: 54% busy in the 16x16 search) is the busier one, the FMA pipe idles at 16%.
 // 4K 10-bit 62.5 -> 63.4 frames/s.
@@ -682,7 +686,7 @@ template <typename T, int W, bool SKIP, bool TMAF>
 __device__ __forceinline__ unsigned diamond_search(const Search<T> &S_in, MV2 start, int search_step, int *num00,
                                                 MV2 *best_out) {
   using L = SadL<T, W, SKIP>;
-  constexpr int PU = (W == 32) ? 2 : (L::MAXP < 3 ? L::MAXP : 3);  // passes whose loads are issued back to back
+  constexpr int PU = (W == 32) ? 2 : (L::MAXP < TF_PU16 ? L::MAXP : TF_PU16);  // passes whose loads are issued back to back
   const Search<T> S = S_in;
   const int lane = lane_id();
   const int grp = lane / L::LPC, row = (lane % L::LPC) * L::RSTEP;
@@ -1934,8 +1938,9 @@ __device__ __noinline__ void convolve12_packed(const KParams &P, const uint16_t 
 
 // The filter kernel runs FILT_WARPS = 4 warps per 32x32 block: warp q builds the predictor of
 // sub-block q of every plane (its own MV), the element-wise stages stride over all threads.
+// seven blocks per SM (73 registers, 48 bytes of spills): filter 2.70 -> 2.64 ms at 4K 10-bit, 0.57 -> 0.51 ms at 1080p 8-bit
 #ifndef TF_FILT_MINB
-#define TF_FILT_MINB 6
+#define TF_FILT_MINB 7
 #endif
 constexpr int FILT_WARPS = 4;
 constexpr int FILT_THREADS = FILT_WARPS * 32;
